@@ -1,0 +1,947 @@
+// Hand-written sm_100a kernels of the PGURE-SVT hot path.  Each kernel cites the reference code it replaces
+// (file:line relative to tjof2/pgure-svt v0.6.4).  All arithmetic the reference does in double stays FP64;
+// tensor cores are not used (the per-patch matrices are 16x15 … 256x15, not a dense contraction).
+//
+// Device data layout (column-major like Armadillo):
+//   frames      X[r + N*(c + N*f)]                      native input type (u8/u16/f32/f64)
+//   window      u, w  double (N, N, win)                normalised by the window maximum (pguresvt.hpp:116-120)
+//   pos         short2[k*vecSize + id]  (.x=row,.y=col) trajectories = arma::icube patches(2, vecSize, win)
+//   mot         short2[s*vecSize + id]                  motions(2, vecSize, win-1)
+//   factors     per patch one record of REC doubles: U (m x n) | V (ldv x n, rows >= n zero) | S (ldv, descending)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pgs
+{
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ double to_double(T v)
+{
+    return (double)v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// frame maxima  (u.max(), w.max(): pguresvt.hpp:116-117) — per-frame partial maxima, combined per window
+// on the host.  grid = (bpf, nframes)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_frame_max(const T *__restrict__ X, size_t fsz, double *__restrict__ partial)
+{
+    const T *f = X + fsz * blockIdx.y;
+    double m = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < fsz; i += (size_t)gridDim.x * blockDim.x)
+        m = fmax(m, to_double(f[i]));
+    m = warp_max(m);
+    __shared__ double sm[32];
+    if ((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : -INFINITY;
+        m = warp_max(m);
+        if (threadIdx.x == 0)
+            partial[blockIdx.y * gridDim.x + blockIdx.x] = m;
+    }
+}
+
+// conv_to<Mat<uint16_t>>::from(X.slice(i))  (pguresvt.hpp:75)
+template <typename T>
+__global__ void k_to_u16(const T *__restrict__ X, uint16_t *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (uint16_t)X[i];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_median — (2r+1)^2 clamp-to-edge median of uint16, the result of ConstantTimeMedianFilter
+// (medfilter.hpp:478-539 as called at pguresvt.hpp:75-76).  One CTA = 32x32 output tile staged
+// (with halo) in shared memory; each pixel selects its median by a 16-step bitwise search over the value
+// (count of window entries below the candidate), so no per-thread sort or histogram is needed.
+// grid = (ceil(N/32), ceil(N/32), nframes), block = (32, 8)
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_median_u16(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int nr, int nc, int r)
+{
+    extern __shared__ uint16_t tile[];
+    const int tw = 32 + 2 * r;
+    const size_t fsz = (size_t)nr * nc;
+    const uint16_t *s = src + fsz * blockIdx.z;
+    uint16_t *d = dst + fsz * blockIdx.z;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int idx = tid; idx < tw * tw; idx += 256)
+    {
+        const int tr = idx % tw, tc = idx / tw;
+        const int gr = min(max(r0 + tr - r, 0), nr - 1);
+        const int gc = min(max(c0 + tc - r, 0), nc - 1);
+        tile[idx] = s[gr + (size_t)nr * gc];
+    }
+    __syncthreads();
+    const int K = (2 * r + 1) * (2 * r + 1), kth = K / 2, wdt = 2 * r + 1;
+    const int lr = threadIdx.x;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; cc++)
+    {
+        const int lc = threadIdx.y + 8 * cc;
+        if (r0 + lr >= nr || c0 + lc >= nc)
+            continue;
+        unsigned prefix = 0;
+#pragma unroll 1
+        for (int bit = 15; bit >= 0; bit--)
+        {
+            const unsigned cand = prefix | (1u << bit);
+            int cnt = 0;
+            for (int dc = 0; dc < wdt; dc++)
+            {
+                const uint16_t *col = tile + lr + tw * (lc + dc);
+                for (int dr = 0; dr < wdt; dr++)
+                    cnt += (col[dr] < cand) ? 1 : 0;
+            }
+            if (cnt <= kth)
+                prefix = cand;
+        }
+        d[(r0 + lr) + (size_t)nr * (c0 + lc)] = (uint16_t)prefix;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_window — u = conv_to<cube>(X.slices(a,b)) / uMax  (pguresvt.hpp:100-120).  True division, like arma's
+// `cube /= scalar`.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_window(const T *__restrict__ X, double *__restrict__ u, size_t n, double vmax)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        u[i] = __ddiv_rn(to_double(X[i]), vmax);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_perturb — Bernoulli perturbations of PGURE::GenerateRandomPerturbations (pgure.hpp:167-186) drawn from
+// pcg64 = setseq_xsl_rr_128_64 (pcg_random.hpp:166-169,427-451,1085-1113) through libstdc++'s
+// bernoulli_distribution, bit-identically: draw g (all of delta1 first, then delta2, column-major) uses the
+// generator state after g+1 steps, reached by the O(log g) LCG jump-ahead (pcg_random.hpp:471-474), so the
+// stream is generated in parallel.
+// ------------------------------------------------------------------------------------------------------
+struct U128
+{
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 mul128(U128 a, U128 b)
+{
+    U128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = __umul64hi(a.lo, b.lo) + a.lo * b.hi + a.hi * b.lo;
+    return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b)
+{
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+#define PCG_MULT_HI 2549297995355413924ull
+#define PCG_MULT_LO 4865540595714422341ull
+#define PCG_INC_HI 6364136223846793005ull
+#define PCG_INC_LO 1442695040888963407ull
+
+__global__ void k_perturb(int8_t *__restrict__ d1, int8_t *__restrict__ d2neg, long long n, unsigned long long seed,
+                          double vP, int chunk)
+{
+    const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)chunk;
+    if (start >= 2 * n)
+        return;
+    const U128 MULT = {PCG_MULT_LO, PCG_MULT_HI}, INC = {PCG_INC_LO, PCG_INC_HI};
+    U128 st = {seed, 0ull};
+    st = add128(mul128(add128(st, INC), MULT), INC); // engine(seed): state = (seed + inc)*mult + inc
+    { // advance by `start` steps
+        U128 acc_mult = {1ull, 0ull}, acc_plus = {0ull, 0ull}, cur_mult = MULT, cur_plus = INC;
+        unsigned long long delta = (unsigned long long)start;
+        while (delta > 0)
+        {
+            if (delta & 1)
+            {
+                acc_mult = mul128(acc_mult, cur_mult);
+                acc_plus = add128(mul128(acc_plus, cur_mult), cur_plus);
+            }
+            U128 one = {1ull, 0ull};
+            cur_plus = mul128(add128(cur_mult, one), cur_plus);
+            cur_mult = mul128(cur_mult, cur_mult);
+            delta >>= 1;
+        }
+        st = add128(mul128(acc_mult, st), acc_plus);
+    }
+    for (int j = 0; j < chunk; j++)
+    {
+        const long long g = start + j;
+        if (g >= 2 * n)
+            break;
+        st = add128(mul128(st, MULT), INC);
+        const unsigned rot = (unsigned)(st.hi >> 58);
+        const unsigned long long x = st.hi ^ st.lo;
+        const unsigned long long out = (x >> rot) | (x << ((64 - rot) & 63));
+        double uu = __ull2double_rn(out) * 5.42101086242752217e-20; // * 2^-64
+        if (uu >= 1.0)
+            uu = 0.99999999999999989;
+        if (g < n)
+            d1[g] = (uu < 0.5) ? (int8_t)-1 : (int8_t)1;
+        else
+            d2neg[g - n] = (uu < vP) ? (int8_t)1 : (int8_t)0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_arps — adaptive rood pattern search, one thread per macroblock, one launch per frame pair in the
+// reference's order (arps.hpp:52-134 schedules, :153-375 search).  The block cost is evaluated exactly like
+// arma::accu(square(A-B)) * (1/bs^2) (arps.hpp:148-151): two running sums over even/odd column-major linear
+// indices, added at the end, no FMA contraction — motion vectors must be bit-exact.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double arps_cost(const double *__restrict__ A1, const double *__restrict__ A2, int N, int bs,
+                                            int ry, int rx, int py, int px, double oobs2)
+{
+    double v1 = 0.0, v2 = 0.0;
+    int e = 0;
+    for (int c = 0; c < bs; c++)
+    {
+        const double *a = A1 + ry + (size_t)N * (rx + c);
+        const double *b = A2 + py + (size_t)N * (px + c);
+        for (int r = 0; r < bs; r++, e++)
+        {
+            const double d = __dsub_rn(a[r], b[r]);
+            const double sq = __dmul_rn(d, d);
+            if (e & 1)
+                v2 = __dadd_rn(v2, sq);
+            else
+                v1 = __dadd_rn(v1, sq);
+        }
+    }
+    return __dmul_rn(__dadd_rn(v1, v2), oobs2);
+}
+
+#define ARPS_MAX_MW 15
+__global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw, int f1, int f2, int f3,
+                            short2 *__restrict__ pos, short2 *__restrict__ mot, int vecSize, double oobs2,
+                            unsigned long long *__restrict__ ncost)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= vecSize)
+        return;
+    const int M1 = N - bs + 1;
+    const int i = it % M1, j = it / M1;
+    const size_t fsz = (size_t)N * N;
+    const double *A1 = w + fsz * f1, *A2 = w + fsz * f2;
+    const int W = 2 * mw + 1;
+    unsigned chk[(2 * ARPS_MAX_MW + 1) * (2 * ARPS_MAX_MW + 1) / 32 + 1];
+#pragma unroll
+    for (int q = 0; q < (2 * ARPS_MAX_MW + 1) * (2 * ARPS_MAX_MW + 1) / 32 + 1; q++)
+        chk[q] = 0u;
+#define CHK_SET(cy, cx)                                \
+    {                                                  \
+        const int b_ = (cy) + W * (cx);                \
+        chk[b_ >> 5] |= 1u << (b_ & 31);               \
+    }
+#define CHK_GET(cy, cx) ((chk[((cy) + W * (cx)) >> 5] >> (((cy) + W * (cx)) & 31)) & 1u)
+    const int SDx[5] = {0, -1, 0, 1, 0}, SDy[5] = {-1, 0, 0, 0, 1}; // (hor, ver) offsets, arps.hpp:174-184
+    double costs[6];
+    int LDx[6], LDy[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+        costs[k] = 1E9;
+        LDx[k] = 0;
+        LDy[k] = 0;
+    }
+    int x = j, y = i;
+    unsigned nc = 1;
+    costs[2] = arps_cost(A1, A2, N, bs, i, j, i, j, oobs2);
+    CHK_SET(mw, mw);
+    int maxIdx, stepSize;
+    if (j == 0)
+    {
+        stepSize = 2;
+        maxIdx = 5;
+    }
+    else
+    {
+        const short2 pm = mot[(size_t)f3 * vecSize + it];
+        const int yTmp = abs((int)pm.x), xTmp = abs((int)pm.y);
+        stepSize = (xTmp <= yTmp) ? yTmp : xTmp;
+        if (((yTmp == 0) && (xTmp == stepSize)) || ((xTmp == 0) && (yTmp == stepSize)))
+            maxIdx = 5;
+        else
+        {
+            maxIdx = 6;
+            LDx[5] = pm.y;
+            LDy[5] = pm.x;
+        }
+    }
+    LDx[0] = 0, LDy[0] = -stepSize;
+    LDx[1] = -stepSize, LDy[1] = 0;
+    LDx[2] = 0, LDy[2] = 0;
+    LDx[3] = stepSize, LDy[3] = 0;
+    LDx[4] = 0, LDy[4] = stepSize;
+    for (int k = 0; k < maxIdx; k++) // LDSP, arps.hpp:247-287
+    {
+        const int ver = y + LDy[k], hor = x + LDx[k];
+        const bool skip = (k == 2) || (stepSize == 0) || (hor < 0) || (ver < 0) || (hor + bs - 1) >= N || (ver + bs - 1) >= N;
+        if (!skip)
+        {
+            costs[k] = arps_cost(A1, A2, N, bs, i, j, ver, hor, oobs2);
+            nc++;
+            const int cy = LDy[k] + mw, cx = LDx[k] + mw;
+            if (cy >= 0 && cy < W && cx >= 0 && cx < W)
+                CHK_SET(cy, cx);
+        }
+    }
+    int point = 0;
+#pragma unroll
+    for (int k = 1; k < 6; k++)
+        if (costs[k] < costs[point])
+            point = k;
+    x += LDx[point];
+    y += LDy[point];
+    double cost = costs[point];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        costs[k] = 1E9;
+    costs[2] = cost;
+    bool done = false;
+    unsigned nSDSP = 0;
+    do // SDSP, arps.hpp:299-368
+    {
+        for (int k = 0; k < 5; k++)
+        {
+            const int ver = y + SDy[k], hor = x + SDx[k];
+            bool skip = (k == 2) || (hor < 0) || (ver < 0) || (hor + bs - 1) >= N || (ver + bs - 1) >= N || (hor < j - mw) ||
+                        (hor > j + mw) || (ver < i - mw) || (ver > i + mw);
+            if (!skip)
+                skip = CHK_GET(y - i + SDy[k] + mw, x - j + SDx[k] + mw) != 0u;
+            if (!skip)
+            {
+                costs[k] = arps_cost(A1, A2, N, bs, i, j, ver, hor, oobs2);
+                nc++;
+                CHK_SET(y - i + SDy[k] + mw, x - j + SDx[k] + mw);
+            }
+        }
+        point = 0;
+#pragma unroll
+        for (int k = 1; k < 6; k++)
+            if (costs[k] < costs[point])
+                point = k;
+        cost = costs[point];
+        if (point == 2 || nSDSP >= 1000000u)
+            done = true;
+        else
+        {
+            x += SDx[point];
+            y += SDy[point];
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                costs[k] = 1E9;
+            costs[2] = cost;
+        }
+        nSDSP++;
+    } while (!done);
+    mot[(size_t)f3 * vecSize + it] = make_short2((short)(y - i), (short)(x - j));
+    pos[(size_t)f2 * vecSize + it] = make_short2((short)y, (short)x);
+    if (ncost)
+        atomicAdd(ncost, (unsigned long long)nc);
+#undef CHK_SET
+#undef CHK_GET
+}
+
+// reference coordinates of the window's reference slice (arps.hpp:60-64)
+__global__ void k_seed_pos(short2 *__restrict__ pos, int vecSize, int M1, int ref)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it < vecSize)
+        pos[(size_t)ref * vecSize + it] = make_short2((short)(it % M1), (short)(it / M1));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_count — `weights` of SVT::Reconstruct (svt.hpp:156-159): number of patches covering each voxel.  It is
+// independent of lambda and of the SVT object, so it is computed once per frame.  One thread per (patch, k).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_count(const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, int bs,
+                        int win, int only_k, unsigned *__restrict__ cnt)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nk = (only_k >= 0) ? 1 : win;
+    if (t >= (long long)P * nk)
+        return;
+    const int pi = (int)(t % P);
+    const int k = (only_k >= 0) ? only_k : (int)(t / P);
+    const short2 p = pos[(size_t)k * vecSize + ids[pi]];
+    unsigned *c0 = cnt + (size_t)N * N * k;
+    for (int c = 0; c < bs; c++)
+        for (int r = 0; r < bs; r++)
+            atomicAdd(c0 + (p.x + r) + (size_t)N * (p.y + c), 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Casorati gather shared by the SVD kernels (svt.hpp:99-109) with the PGURE perturbations applied on the fly
+// (pgure.hpp:80-82): mode 0: U; 1: U + delta1*eps1; 2: U + delta2*eps2; 3: U - delta2*eps2.
+// ------------------------------------------------------------------------------------------------------
+struct Perturb
+{
+    const int8_t *d1;
+    const int8_t *d2neg;
+    int mode;
+    double eps;  // eps1 or eps2
+    double dNeg; // -sqrt(vQ/vP)
+    double dPos; // +sqrt(vP/vQ)
+};
+__device__ __forceinline__ double load_perturbed(const double *__restrict__ u, size_t vox, const Perturb &pt)
+{
+    double v = u[vox];
+    if (pt.mode == 1)
+        v = __dadd_rn(v, __dmul_rn((double)pt.d1[vox], pt.eps));
+    else if (pt.mode >= 2)
+    {
+        const double t = __dmul_rn(pt.d2neg[vox] ? pt.dNeg : pt.dPos, pt.eps);
+        v = (pt.mode == 2) ? __dadd_rn(v, t) : __dsub_rn(v, t);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void jacobi_cs(double A, double B, double G, double tol2, double &c, double &s, bool &rot)
+{
+    c = 1.0;
+    s = 0.0;
+    if (G * G > tol2 * A * B)
+    {
+        const double d = B - A;
+        const double h = sqrt(d * d + 4.0 * G * G);
+        const double t = ((d >= 0.0) ? 2.0 * G : -2.0 * G) / (fabs(d) + h);
+        c = rsqrt(1.0 + t * t);
+        s = c * t;
+        rot = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_svd (generic) — thin SVD of every patch's Casorati matrix (arma::svd_econ, svt.hpp:111) by one-sided
+// Jacobi, one warp per matrix, matrix and V in shared memory.  Any m = bs^2, n = win.  Fallback for the
+// shapes the register kernel below does not cover (e.g. 256x15, 64x31).
+// dynamic smem per warp: (m*n + n*n + n) doubles.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_svd_smem(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos,
+                           const int *__restrict__ ids, int P, int vecSize, int N, int bs, int n, int ldv,
+                           double *__restrict__ fac, size_t rec, int max_sweeps, double tol2, int *__restrict__ sweeps_out)
+{
+    extern __shared__ double smd[];
+    const int m = bs * bs;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pidx = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (pidx >= P)
+        return;
+    double *A = smd + (size_t)wib * (m * n + n * n + n);
+    double *V = A + m * n;
+    double *sig = V + n * n;
+    const int id = ids[pidx];
+    const size_t fsz = (size_t)N * N;
+    for (int k = 0; k < n; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        for (int e = lane; e < m; e += 32)
+        {
+            const int r = e % bs, c = e / bs;
+            A[e + m * k] = load_perturbed(u, (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k, pt);
+        }
+    }
+    for (int e = lane; e < n * n; e += 32)
+        V[e] = ((e % n) == (e / n)) ? 1.0 : 0.0;
+    __syncwarp();
+    int sweep = 0;
+    for (; sweep < max_sweeps; sweep++)
+    {
+        bool rotated = false;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++)
+            {
+                double a = 0, b = 0, g = 0;
+                for (int e = lane; e < m; e += 32)
+                {
+                    const double x = A[e + m * p], y = A[e + m * q];
+                    a = fma(x, x, a);
+                    b = fma(y, y, b);
+                    g = fma(x, y, g);
+                }
+                a = warp_sum(a);
+                b = warp_sum(b);
+                g = warp_sum(g);
+                double c, s;
+                bool rot = false;
+                jacobi_cs(a, b, g, tol2, c, s, rot);
+                if (rot)
+                {
+                    rotated = true;
+                    for (int e = lane; e < m; e += 32)
+                    {
+                        const double x = A[e + m * p], y = A[e + m * q];
+                        A[e + m * p] = c * x - s * y;
+                        A[e + m * q] = s * x + c * y;
+                    }
+                    for (int e = lane; e < n; e += 32)
+                    {
+                        const double x = V[e + n * p], y = V[e + n * q];
+                        V[e + n * p] = c * x - s * y;
+                        V[e + n * q] = s * x + c * y;
+                    }
+                }
+                __syncwarp();
+            }
+        if (!rotated)
+            break;
+    }
+    for (int j = 0; j < n; j++)
+    {
+        double a = 0;
+        for (int e = lane; e < m; e += 32)
+            a = fma(A[e + m * j], A[e + m * j], a);
+        a = warp_sum(a);
+        if (lane == 0)
+            sig[j] = sqrt(a);
+    }
+    __syncwarp();
+    double *R = fac + rec * (size_t)pidx;
+    for (int j = 0; j < n; j++)
+    {
+        const double sj = sig[j];
+        int rk = 0;
+        for (int t = 0; t < n; t++)
+            rk += (sig[t] > sj || (sig[t] == sj && t < j)) ? 1 : 0;
+        const double inv = (sj > 0.0) ? 1.0 / sj : 0.0;
+        for (int e = lane; e < m; e += 32)
+            R[e + (size_t)m * rk] = A[e + m * j] * inv;
+        for (int e = lane; e < n; e += 32)
+            R[(size_t)m * n + e + (size_t)ldv * rk] = V[e + n * j];
+        if (lane == 0)
+            R[(size_t)m * n + (size_t)ldv * n + rk] = sj;
+    }
+    if (lane == 0 && sweeps_out)
+        atomicMax(sweeps_out, sweep + 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_svd (register) — 16x15 Casorati matrices (bs = 4, win = 15: the headline configuration).
+// Eight lanes per matrix, four matrices per warp.  Lane j of a group keeps rows 2j, 2j+1 of A (16 x 16 with a
+// zero 16th column) and of V in registers.  A sweep is 15 rounds of the round-robin (Brent–Luk) ordering: in
+// every round the 8 slot pairs (2i, 2i+1) are orthogonalised at once —
+//   * 24 partial dot products per lane (alpha, beta, gamma of the 8 pairs over the lane's two rows),
+//   * ONE transposing butterfly over the 8 lanes (7 shuffles per quantity) that leaves lane i with the three
+//     sums of pair i, so each lane derives a single rotation (one sqrt, one divide, one rsqrt),
+//   * (c, s) of pair i broadcast from lane i, rotations applied to the lane's rows of A and V,
+//   * columns move one slot along the round-robin cycle (register renaming; slot 0 is fixed).
+// After 15 rounds every column is back in its home slot, so convergence is tested per sweep with one vote.
+// Singular values are sorted descending and U = A·V/sigma is written with V and S (LAPACK's order, svt.hpp:111).
+// ------------------------------------------------------------------------------------------------------
+#define SVD16_M 16
+#define SVD16_N 15
+#define SVD16_LDV 16
+#define SVD16_REC (SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + SVD16_LDV) /* 496 doubles */
+
+__device__ __forceinline__ double tr8(const double (&x)[8], int sub)
+{
+    // transposing reduction of 8 values over the 8 lanes of a group: lane `sub` returns sum over lanes of x[sub]
+    double y[4], z[2];
+    const bool h4 = (sub & 4) != 0, h2 = (sub & 2) != 0, h1 = (sub & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const double send = h4 ? x[j] : x[j + 4];
+        const double keep = h4 ? x[j + 4] : x[j];
+        y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+    {
+        const double send = h2 ? y[j] : y[j + 2];
+        const double keep = h2 ? y[j + 2] : y[j];
+        z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const double send = h1 ? z[0] : z[1];
+    const double keep = h1 ? z[1] : z[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__global__ void __launch_bounds__(128)
+    k_svd_16x15(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids,
+                int P, int vecSize, int N, double *__restrict__ fac, int max_sweeps, double tol2,
+                int *__restrict__ sweeps_out)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & 7;
+    int pidx = gtid >> 3;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1; // keep the lanes alive for the shuffles; nothing is written
+    const int id = ids[pidx];
+    const size_t fsz = (size_t)N * N;
+    const int e0 = 2 * sub;
+    const int pr = e0 & 3, pc = e0 >> 2;
+
+    double a0[16], a1[16], v0[16], v1[16];
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        const size_t vox = (size_t)(p.x + pr) + (size_t)N * (p.y + pc) + fsz * k;
+        a0[k] = load_perturbed(u, vox, pt);
+        a1[k] = load_perturbed(u, vox + 1, pt);
+    }
+    a0[15] = 0.0;
+    a1[15] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+    {
+        v0[j] = (j == e0) ? 1.0 : 0.0;
+        v1[j] = (j == e0 + 1) ? 1.0 : 0.0;
+    }
+
+    int sweep = 0;
+#pragma unroll 1
+    for (; sweep < max_sweeps; sweep++)
+    {
+        bool rot = false;
+#pragma unroll 1
+        for (int round = 0; round < 15; round++)
+        {
+            double pa[8], pb[8], pg[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                const double x0 = a0[2 * i], y0 = a0[2 * i + 1], x1 = a1[2 * i], y1 = a1[2 * i + 1];
+                pa[i] = fma(x1, x1, x0 * x0);
+                pb[i] = fma(y1, y1, y0 * y0);
+                pg[i] = fma(x1, y1, x0 * y0);
+            }
+            const double A = tr8(pa, sub), B = tr8(pb, sub), G = tr8(pg, sub);
+            double c, s;
+            jacobi_cs(A, B, G, tol2, c, s, rot);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                const double ci = __shfl_sync(0xffffffffu, c, i, 8);
+                const double si = __shfl_sync(0xffffffffu, s, i, 8);
+                double x, y;
+                x = a0[2 * i], y = a0[2 * i + 1];
+                a0[2 * i] = fma(ci, x, -si * y);
+                a0[2 * i + 1] = fma(si, x, ci * y);
+                x = a1[2 * i], y = a1[2 * i + 1];
+                a1[2 * i] = fma(ci, x, -si * y);
+                a1[2 * i + 1] = fma(si, x, ci * y);
+                x = v0[2 * i], y = v0[2 * i + 1];
+                v0[2 * i] = fma(ci, x, -si * y);
+                v0[2 * i + 1] = fma(si, x, ci * y);
+                x = v1[2 * i], y = v1[2 * i + 1];
+                v1[2 * i] = fma(ci, x, -si * y);
+                v1[2 * i + 1] = fma(si, x, ci * y);
+            }
+            // round-robin move: top slots t_i = 2i, bottom b_i = 2i+1; t0 fixed;
+            // t1 <- b0, t_i <- t_{i-1} (i>=2), b_i <- b_{i+1} (i<=6), b7 <- t7
+#define RR_MOVE(X)                 \
+    {                              \
+        const double b0_ = X[1];   \
+        const double t7_ = X[14];  \
+        X[14] = X[12];             \
+        X[12] = X[10];             \
+        X[10] = X[8];              \
+        X[8] = X[6];               \
+        X[6] = X[4];               \
+        X[4] = X[2];               \
+        X[2] = b0_;                \
+        X[1] = X[3];               \
+        X[3] = X[5];               \
+        X[5] = X[7];               \
+        X[7] = X[9];               \
+        X[9] = X[11];              \
+        X[11] = X[13];             \
+        X[13] = X[15];             \
+        X[15] = t7_;               \
+    }
+            RR_MOVE(a0)
+            RR_MOVE(a1)
+            RR_MOVE(v0)
+            RR_MOVE(v1)
+#undef RR_MOVE
+        }
+        if (!__any_sync(0xffffffffu, rot))
+        {
+            sweep++;
+            break;
+        }
+    }
+
+    // singular values: lane `sub` ends up with the squared norms of columns 2*sub and 2*sub+1
+    double n2[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        n2[j] = fma(a1[j], a1[j], a0[j] * a0[j]);
+    double q8[8], q4[4], q2[2];
+    {
+        const bool h4 = (sub & 4) != 0, h2 = (sub & 2) != 0, h1 = (sub & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            const double send = h4 ? n2[j] : n2[j + 8];
+            const double keep = h4 ? n2[j + 8] : n2[j];
+            q8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const double send = h2 ? q8[j] : q8[j + 4];
+            const double keep = h2 ? q8[j + 4] : q8[j];
+            q4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+        {
+            const double send = h1 ? q4[j] : q4[j + 2];
+            const double keep = h1 ? q4[j + 2] : q4[j];
+            q2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+    const double s_lo = sqrt(q2[0]), s_hi = sqrt(q2[1]); // columns 2*sub, 2*sub+1
+    double sig[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        sig[j] = __shfl_sync(0xffffffffu, (j & 1) ? s_hi : s_lo, j >> 1, 8);
+
+    double *R = fac + (size_t)SVD16_REC * pidx;
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+    {
+        int rk = 0;
+#pragma unroll
+        for (int t = 0; t < SVD16_N; t++)
+            rk += (sig[t] > sig[j] || (sig[t] == sig[j] && t < j)) ? 1 : 0;
+        const double inv = (sig[j] > 0.0) ? 1.0 / sig[j] : 0.0;
+        if (valid)
+        {
+            *reinterpret_cast<double2 *>(R + e0 + SVD16_M * rk) = make_double2(a0[j] * inv, a1[j] * inv);
+            *reinterpret_cast<double2 *>(R + SVD16_M * SVD16_N + e0 + SVD16_LDV * rk) = make_double2(v0[j], v1[j]);
+            if ((j >> 1) == sub)
+                R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + rk] = sig[j];
+        }
+    }
+    if (sweeps_out && (threadIdx.x & 31) == 0)
+        atomicMax(sweeps_out, sweep);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_recon — SVT::Reconstruct (svt.hpp:121-160) for one SVT object: threshold the cached singular values
+// (plain lambda, or the exponential weighting of svt.hpp:135-143 with SoftThreshold of utils.hpp:96-106),
+// rebuild block = U diag(Sthr) V^T (svt.hpp:146) and overlap-add it along the patch trajectory into `acc`
+// (svt.hpp:148-155).  A group of G lanes (G = 16 for bs = 4, else 32) owns one patch: V and the thresholded
+// spectrum are staged in shared memory, each lane rebuilds whole rows of the block in registers.  Columns
+// whose thresholded singular value is zero are skipped (rank-adaptive: they contribute nothing).
+// only_k >= 0 restricts the overlap-add to one slice (the only slice the driver consumes for the final
+// reconstruction, pguresvt.hpp:155-166).
+// ------------------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void k_recon(const double *__restrict__ fac, size_t rec, int m, int n, int ldv, int bs,
+                        const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
+                        double lambda, int expw, int only_k, double *__restrict__ acc, int G)
+{
+    extern __shared__ double smr[];
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G, g = threadIdx.x % G;
+    const int pidx = blockIdx.x * gpb + gl;
+    const bool valid = pidx < P;
+    const size_t per = (size_t)ldv * n + NMAX + NMAX; // V | f | pos (short2 packed in doubles' space)
+    double *sV = smr + per * gl;
+    double *sf = sV + (size_t)ldv * n;
+    short2 *sp = reinterpret_cast<short2 *>(sf + NMAX);
+    const double *R = fac + rec * (size_t)(valid ? pidx : 0);
+    if (valid)
+    {
+        const double *S = R + (size_t)m * n + (size_t)ldv * n;
+        const int id = ids[pidx];
+        double smax = S[0];
+        for (int k = 1; k < n; k++)
+            smax = fmax(smax, S[k]);
+        for (int k = g; k < n; k += G)
+        {
+            const double s = S[k];
+            double f;
+            if (expw)
+            {
+                const double w = fabs(smax * exp(-0.5 * lambda * (s * s)));
+                f = fmax(fabs(s) - w, 0.0);
+            }
+            else
+                f = fmax(fabs(s) - lambda, 0.0);
+            sf[k] = (s < 0.0) ? -f : f;
+            sp[k] = pos[(size_t)k * vecSize + id];
+        }
+        const double *Vg = R + (size_t)m * n;
+        for (int e = g; e < ldv * n; e += G)
+            sV[e] = Vg[e];
+    }
+    __syncthreads();
+    if (!valid)
+        return;
+    const size_t fsz = (size_t)N * N;
+    for (int e = g; e < m; e += G)
+    {
+        double a[NMAX];
+#pragma unroll
+        for (int k = 0; k < NMAX; k++)
+            a[k] = 0.0;
+        for (int kk = 0; kk < n; kk++)
+        {
+            const double fk = sf[kk];
+            if (fk != 0.0)
+            {
+                const double uf = R[e + (size_t)m * kk] * fk;
+                const double *vc = sV + (size_t)ldv * kk;
+#pragma unroll
+                for (int k = 0; k < NMAX; k++)
+                    if (k < n)
+                        a[k] = fma(uf, vc[k], a[k]);
+            }
+        }
+        const int r = e % bs, c = e / bs;
+#pragma unroll
+        for (int k = 0; k < NMAX; k++)
+            if (k < n && (only_k < 0 || k == only_k))
+            {
+                const short2 p = sp[k];
+                atomicAdd(acc + (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k, a[k]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_risk — `v /= weights; non-finite -> 0` (svt.hpp:163-164) for the four reconstructions fused with the five
+// global sums of PGURE::CalculatePGURE (pgure.hpp:136).  Fixed grid, fixed-order block reduction → the sums
+// are deterministic given the accumulators.  partial: gridDim.x * 5 doubles.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double norm_or_zero(double a, unsigned c)
+{
+    const double v = a / (double)c;
+    return isfinite(v) ? v : 0.0;
+}
+
+__global__ void k_risk(const double *__restrict__ u, const int8_t *__restrict__ d1, const int8_t *__restrict__ d2neg,
+                       const unsigned *__restrict__ cnt, const double *__restrict__ acc0, const double *__restrict__ acc1,
+                       const double *__restrict__ acc2p, const double *__restrict__ acc2m, size_t tot, double alpha,
+                       double mu, double sigmasq, double dNeg, double dPos, double *__restrict__ partial)
+{
+    double s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const unsigned c = cnt[i];
+        const double U = u[i];
+        const double v0 = norm_or_zero(acc0[i], c);
+        const double v2p = norm_or_zero(acc2p[i], c);
+        const double v2m = norm_or_zero(acc2m[i], c);
+        const double d = fabs(v0 - U);
+        s1 += d * d;
+        s2 += U;
+        if (acc1)
+        {
+            const double v1 = norm_or_zero(acc1[i], c);
+            s3 += ((double)d1[i] * (alpha * U - alpha * mu + sigmasq)) * (v1 - v0);
+        }
+        s4 += (d2neg[i] ? dNeg : dPos) * (v2p - 2 * v0 + v2m);
+        s5 += v0;
+    }
+    __shared__ double sm[5][32];
+    double vals[5] = {s1, s2, s3, s4, s5};
+#pragma unroll
+    for (int q = 0; q < 5; q++)
+    {
+        const double r = warp_sum(vals[q]);
+        if ((threadIdx.x & 31) == 0)
+            sm[q][threadIdx.x >> 5] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+        {
+            double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
+            r = warp_sum(r);
+            if (threadIdx.x == 0)
+                partial[(size_t)blockIdx.x * 5 + q] = r;
+        }
+    }
+}
+
+// final fixed-order reduction of the per-block partial sums: one block, nq quantities
+__global__ void k_reduce_partials(const double *__restrict__ partial, int nblocks, int nq, double *__restrict__ out)
+{
+    __shared__ double sm[32];
+    for (int q = 0; q < nq; q++)
+    {
+        double r = 0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+            r += partial[(size_t)b * nq + q];
+        r = warp_sum(r);
+        if ((threadIdx.x & 31) == 0)
+            sm[threadIdx.x >> 5] = r;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+            r = warp_sum(r);
+            if (threadIdx.x == 0)
+                out[q] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// sum of a double array (accu(u), pguresvt.hpp:139) → partial[gridDim.x]
+__global__ void k_sum(const double *__restrict__ x, size_t n, double *__restrict__ partial)
+{
+    double s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        s += x[i];
+    s = warp_sum(s);
+    __shared__ double sm[32];
+    if ((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+        if (threadIdx.x == 0)
+            partial[blockIdx.x] = s;
+    }
+}
+
+// v = acc / weights, non-finite -> 0, times scale (svt.hpp:163-164, pguresvt.hpp:147); n voxels starting at
+// offset `off` of acc/cnt, written to out[0..n)
+__global__ void k_finalize(const double *__restrict__ acc, const unsigned *__restrict__ cnt, size_t off, size_t n,
+                           double scale, double *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = norm_or_zero(acc[off + i], cnt[off + i]) * scale;
+}
+
+} // namespace pgs

@@ -1,0 +1,1128 @@
+// C-ABI + host driver of the B200-native PGURE-SVT hot path (include/pguresvt_b200.h).
+//
+// The driver restates the control flow of PGURESVT<T1,T2>() (src/pguresvt.hpp:17-172): median prefilter of
+// every frame, then per output frame: window normalisation, (noise estimation), ARPS trajectories, the patch
+// SVDs of up to four SVT objects cached in HBM, the lambda search where every objective evaluation is
+// threshold + reconstruct + aggregate + risk reduction on the device, the final reconstruction and the copy
+// of the reference slice.  All array work is CUDA; the host only sequences kernels and runs the scalar 1-D
+// optimiser.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include "../../include/pguresvt_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "noise.cuh"
+#include "sbplx1d.hpp"
+
+using namespace pgs;
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+extern "C" const char *pguresvt_last_error(void) { return g_err.c_str(); }
+
+#define CU(call)                                                                                          \
+    do                                                                                                    \
+    {                                                                                                     \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(PGS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------------
+struct pguresvt_handle
+{
+    pguresvt_params p{};
+    int dtype = 0;
+    uint32_t N = 0, nframes = 0, fb = 0, fe = 0; // square frames N x N; block [fb, fe)
+    uint32_t Nt = 0, fw = 0, win = 0;            // pguresvt.hpp:57-58; window has 2*fw+1 slices
+    uint32_t r0 = 0, r1 = 0;                     // resident frames [r0, r1)
+    size_t fsz = 0, esz = 0;
+    int m = 0, n = 0, ldv = 0, M1 = 0, vecSize = 0, P = 0;
+    size_t rec = 0;
+    int nobj = 1;
+    int objs[4] = {0, 0, 0, 0}; // SVT objects present: 0:U 1:U1 2:U2p 3:U2m
+    bool use_reg_svd = false;
+    int sm_count = 148;
+    double vP = 0, d2Neg = 0, d2Pos = 0;
+    int64_t seed_used = 0;
+
+    // device
+    void *dX = nullptr;
+    uint16_t *dZ = nullptr, *dTmp16 = nullptr;
+    double *dU = nullptr, *dW = nullptr;
+    short2 *dPos = nullptr, *dMot = nullptr;
+    int *dIds = nullptr;
+    unsigned *dCnt = nullptr;
+    double *dAcc[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *dFac[4] = {nullptr, nullptr, nullptr, nullptr};
+    int8_t *dD1 = nullptr, *dD2 = nullptr;
+    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr;
+    double *dY = nullptr, *dEst = nullptr, *dV = nullptr;
+    int *dSweeps = nullptr;
+    unsigned long long *dNcost = nullptr;
+    NoiseWorkspace noise_ws;
+    double *hOut = nullptr; // pinned
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    std::vector<double> xmax, zmax; // per resident frame
+    std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
+    bool uploaded = false, prefiltered = false, perturbed = false;
+    long long cur_t = -1;
+    bool cur_opt_ready = false;
+    double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
+    int cur_ref = 0, cur_sl = 0, cur_a = 0;
+    double stats[PGS_NSTATS] = {0};
+    long long launches = 0;
+};
+
+#define RISK_BLOCKS 1184
+#define LAUNCHED(h) ((h)->launches++)
+
+static size_t dtype_size(int dt) { return dt == PGS_U8 ? 1 : dt == PGS_U16 ? 2 : dt == PGS_F32 ? 4 : 8; }
+
+// sorted unique patch ids of SVT::Decompose (svt.hpp:61-97)
+static std::vector<int> patch_ids(int N, int bs, int bo)
+{
+    const long long M = N - bs;
+    std::vector<long long> ids;
+    for (long long i = 0; i < 1 + M; i += bo)
+        for (long long j = 0; j < 1 + M; j += bo)
+            ids.push_back(i * M + j);
+    for (long long i = 0; i < 1 + M; i += bo)
+        ids.push_back((M + 1) * i + M);
+    for (long long i = 0; i < 1 + M; i += bo)
+        ids.push_back((M + 1) * M + i);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    return std::vector<int>(ids.begin(), ids.end());
+}
+
+static uint32_t window_start(const pguresvt_handle *h, uint32_t t) // pguresvt.hpp:100-114
+{
+    if (t < h->fw)
+        return 0;
+    if (t >= h->nframes - h->fw)
+        return h->nframes - 2 * h->fw - 1;
+    return t - h->fw;
+}
+
+static void free_all(pguresvt_handle *h)
+{
+    auto F = [](void *p) {
+        if (p)
+            cudaFree(p);
+    };
+    F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dMot), F(h->dIds), F(h->dCnt);
+    for (int i = 0; i < 4; i++)
+        F(h->dAcc[i]), F(h->dFac[i]);
+    F(h->dD1), F(h->dD2), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
+        F(h->dNcost);
+    h->noise_ws.release();
+    if (h->hOut)
+        cudaFreeHost(h->hOut);
+    if (h->st)
+        cudaStreamDestroy(h->st);
+    for (int i = 0; i < 2; i++)
+        if (h->ev[i])
+            cudaEventDestroy(h->ev[i]);
+}
+
+extern "C" void pguresvt_destroy(pguresvt_handle *h)
+{
+    if (!h)
+        return;
+    cudaSetDevice(h->p.device);
+    free_all(h);
+    delete h;
+}
+
+static int create_impl(pguresvt_handle *h)
+{
+    const pguresvt_params &p = h->p;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PGS_ERR_CUDA, "no CUDA device available (the PGURE-SVT hot path has no CPU fallback)");
+    if (p.device < 0 || p.device >= ndev)
+        return fail(PGS_ERR_ARG, "device %d out of range (%d devices)", p.device, ndev);
+    CU(cudaSetDevice(p.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p.device));
+    h->sm_count = prop.multiProcessorCount;
+
+    const uint32_t bs = p.block_size;
+    if (bs < 1 || bs > h->N)
+        return fail(PGS_ERR_ARG, "patch_size %u invalid for %ux%u frames", bs, h->N, h->N);
+    if (p.block_overlap < 1)
+        return fail(PGS_ERR_ARG, "patch_overlap must be >= 1");
+    h->Nt = (bs * bs < p.traj_length) ? bs * bs - 1 : p.traj_length;
+    h->fw = h->Nt / 2;
+    h->win = 2 * h->fw + 1;
+    if (h->Nt < 1)
+        return fail(PGS_ERR_ARG, "trajectory length / patch size give an empty window");
+    if (h->nframes < h->win)
+        return fail(PGS_ERR_ARG, "sequence has %u frames, fewer than the %u-frame window", h->nframes, h->win);
+    if (h->fb >= h->fe || h->fe > h->nframes)
+        return fail(PGS_ERR_ARG, "invalid frame block [%u, %u) of %u", h->fb, h->fe, h->nframes);
+    if (p.motion_estimation && (p.motion_window > ARPS_MAX_MW))
+        return fail(PGS_ERR_UNSUPPORTED, "motion_window %u > %d not supported by the ARPS kernel", p.motion_window,
+                    ARPS_MAX_MW);
+    if (p.median_size > 60)
+        return fail(PGS_ERR_UNSUPPORTED, "median radius %lld > 60 not supported", (long long)p.median_size);
+    if (h->win > 32)
+        return fail(PGS_ERR_UNSUPPORTED, "window of %u slices > 32 not supported", h->win);
+    if (h->N > 32767)
+        return fail(PGS_ERR_UNSUPPORTED, "frames larger than 32767 px not supported");
+    h->m = bs * bs;
+    h->n = h->win;
+    h->ldv = (h->n + 1) & ~1;
+    h->rec = (size_t)h->m * h->n + (size_t)h->ldv * h->n + h->ldv;
+    h->M1 = h->N - bs + 1;
+    h->vecSize = h->M1 * h->M1;
+    std::vector<int> ids = patch_ids(h->N, bs, p.block_overlap);
+    h->P = (int)ids.size();
+    h->fsz = (size_t)h->N * h->N;
+    h->esz = dtype_size(h->dtype);
+    h->r0 = window_start(h, h->fb);
+    h->r1 = window_start(h, h->fe - 1) + h->win;
+    h->nobj = 0;
+    h->objs[h->nobj++] = 0;
+    if (p.optimize_pgure)
+    {
+        if (p.eps1_mode == 1)
+            h->objs[h->nobj++] = 1;
+        h->objs[h->nobj++] = 2;
+        h->objs[h->nobj++] = 3;
+    }
+    h->use_reg_svd = (h->m == 16 && h->n == 15 && p.svd_kernel != 1);
+    if (p.svd_kernel == 2 && !h->use_reg_svd)
+        return fail(PGS_ERR_UNSUPPORTED, "register SVD kernel only covers 16x15 Casorati matrices");
+    {
+        const double kappa = 1.;
+        h->vP = 0.5 + 0.5 * kappa / std::sqrt(kappa * kappa + 4);
+        const double vQ = 1 - h->vP;
+        h->d2Neg = -1 * std::sqrt(vQ / h->vP);
+        h->d2Pos = std::sqrt(h->vP / vQ);
+    }
+
+    const size_t wtot = h->fsz * h->win;
+    const uint32_t nres = h->r1 - h->r0, nblk = h->fe - h->fb;
+    CU(cudaStreamCreate(&h->st));
+    CU(cudaEventCreate(&h->ev[0]));
+    CU(cudaEventCreate(&h->ev[1]));
+    CU(cudaMalloc(&h->dX, h->fsz * nres * h->esz));
+    if (p.median_size > 0)
+    {
+        CU(cudaMalloc(&h->dZ, h->fsz * nres * sizeof(uint16_t)));
+        if (h->dtype != PGS_U16)
+            CU(cudaMalloc(&h->dTmp16, h->fsz * nres * sizeof(uint16_t)));
+    }
+    CU(cudaMalloc(&h->dU, wtot * sizeof(double)));
+    if (p.motion_estimation)
+        CU(cudaMalloc(&h->dW, wtot * sizeof(double)));
+    CU(cudaMalloc(&h->dPos, (size_t)h->win * h->vecSize * sizeof(short2)));
+    CU(cudaMalloc(&h->dMot, (size_t)h->win * h->vecSize * sizeof(short2)));
+    CU(cudaMalloc(&h->dIds, (size_t)h->P * sizeof(int)));
+    CU(cudaMemcpy(h->dIds, ids.data(), (size_t)h->P * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->dCnt, wtot * sizeof(unsigned)));
+    for (int k = 0; k < h->nobj; k++)
+    {
+        const int o = h->objs[k];
+        CU(cudaMalloc(&h->dAcc[o], wtot * sizeof(double)));
+        CU(cudaMalloc(&h->dFac[o], h->rec * (size_t)h->P * sizeof(double)));
+        CU(cudaMemset(h->dFac[o], 0, h->rec * (size_t)h->P * sizeof(double)));
+    }
+    if (p.optimize_pgure)
+    {
+        CU(cudaMalloc(&h->dD1, wtot));
+        CU(cudaMalloc(&h->dD2, wtot));
+    }
+    CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
+    CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
+    CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
+    CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
+    CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
+    CU(cudaMalloc(&h->dSweeps, sizeof(int)));
+    CU(cudaMalloc(&h->dNcost, sizeof(unsigned long long)));
+    CU(cudaMallocHost(&h->hOut, 16 * sizeof(double)));
+    h->xmax.assign(nres, 0.0);
+    h->zmax.assign(nres, 0.0);
+    h->est.assign((size_t)4 * nblk, 0.0);
+    return PGS_OK;
+}
+
+extern "C" pguresvt_handle *pguresvt_create(int dtype, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames,
+                                            const pguresvt_params *p, uint32_t frame_begin, uint32_t frame_end)
+{
+    g_err.clear();
+    if (!p)
+    {
+        fail(PGS_ERR_ARG, "params is NULL");
+        return nullptr;
+    }
+    if (dtype < PGS_U8 || dtype > PGS_F64)
+    {
+        fail(PGS_ERR_ARG, "unknown dtype %d", dtype);
+        return nullptr;
+    }
+    if (n_rows != n_cols)
+    { // the reference assumes square frames throughout; the CLI rejects others
+        fail(PGS_ERR_ARG, "frame dimensions are not square, got %ux%u", n_cols, n_rows);
+        return nullptr;
+    }
+    pguresvt_handle *h = new pguresvt_handle();
+    h->p = *p;
+    h->dtype = dtype;
+    h->N = n_rows;
+    h->nframes = n_frames;
+    h->fb = frame_begin;
+    h->fe = frame_end;
+    if (create_impl(h) != PGS_OK)
+    {
+        free_all(h);
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+extern "C" int pguresvt_resident_range(const pguresvt_handle *h, uint32_t *first, uint32_t *last)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    *first = h->r0;
+    *last = h->r1;
+    return PGS_OK;
+}
+
+static int invalidate(pguresvt_handle *h)
+{
+    h->uploaded = true;
+    h->prefiltered = false;
+    h->cur_t = -1;
+    h->cur_opt_ready = false;
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_upload(pguresvt_handle *h, const void *X_full)
+{
+    if (!h || !X_full)
+        return fail(PGS_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    const char *src = (const char *)X_full + h->fsz * h->r0 * h->esz;
+    CU(cudaMemcpyAsync(h->dX, src, h->fsz * (h->r1 - h->r0) * h->esz, cudaMemcpyHostToDevice, h->st));
+    return invalidate(h);
+}
+
+extern "C" int pguresvt_upload_device(pguresvt_handle *h, const void *dX_resident)
+{
+    if (!h || !dX_resident)
+        return fail(PGS_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaMemcpyAsync(h->dX, dX_resident, h->fsz * (h->r1 - h->r0) * h->esz, cudaMemcpyDeviceToDevice, h->st));
+    return invalidate(h);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// stage: median prefilter + per-frame maxima for all resident frames (pguresvt.hpp:69-88,116-117)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int prefilter_t(pguresvt_handle *h)
+{
+    const uint32_t nres = h->r1 - h->r0;
+    const size_t ntot = h->fsz * nres;
+    const int bpf = 64;
+    std::vector<double> part((size_t)nres * bpf);
+    k_frame_max<T><<<dim3(bpf, nres), 256, 0, h->st>>>((const T *)h->dX, h->fsz, h->dMaxPartial);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(part.data(), h->dMaxPartial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    for (uint32_t f = 0; f < nres; f++)
+        h->xmax[f] = *std::max_element(part.begin() + (size_t)f * bpf, part.begin() + (size_t)(f + 1) * bpf);
+    if (h->p.median_size > 0)
+    {
+        const uint16_t *src16;
+        if (h->dtype == PGS_U16)
+            src16 = (const uint16_t *)h->dX;
+        else
+        {
+            k_to_u16<T><<<std::min(cdiv(ntot, 256), 148 * 16), 256, 0, h->st>>>((const T *)h->dX, h->dTmp16, ntot);
+            LAUNCHED(h);
+            src16 = h->dTmp16;
+        }
+        const int r = (int)h->p.median_size;
+        const int tw = 32 + 2 * r;
+        const size_t smem = (size_t)tw * tw * sizeof(uint16_t);
+        if (smem > 48 * 1024)
+            CU(cudaFuncSetAttribute(k_median_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int nb = cdiv(h->N, 32);
+        k_median_u16<<<dim3(nb, nb, nres), dim3(32, 8), smem, h->st>>>(src16, h->dZ, h->N, h->N, r);
+        LAUNCHED(h);
+        k_frame_max<uint16_t><<<dim3(bpf, nres), 256, 0, h->st>>>(h->dZ, h->fsz, h->dMaxPartial);
+        LAUNCHED(h);
+        CU(cudaMemcpyAsync(part.data(), h->dMaxPartial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        for (uint32_t f = 0; f < nres; f++)
+            h->zmax[f] = *std::max_element(part.begin() + (size_t)f * bpf, part.begin() + (size_t)(f + 1) * bpf);
+    }
+    else
+        h->zmax = h->xmax; // Z = conv_to<cube>(X) (pguresvt.hpp:86)
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+static int prefilter(pguresvt_handle *h)
+{
+    if (h->prefiltered)
+        return PGS_OK;
+    if (!h->uploaded)
+        return fail(PGS_ERR_ARG, "no input uploaded");
+    int rc;
+    switch (h->dtype)
+    {
+    case PGS_U8:
+        rc = prefilter_t<uint8_t>(h);
+        break;
+    case PGS_U16:
+        rc = prefilter_t<uint16_t>(h);
+        break;
+    case PGS_F32:
+        rc = prefilter_t<float>(h);
+        break;
+    default:
+        rc = prefilter_t<double>(h);
+        break;
+    }
+    if (rc == PGS_OK)
+        h->prefiltered = true;
+    return rc;
+}
+
+// Bernoulli perturbations: identical for every frame (same seed, same size: SURVEY Q10) → once per handle
+static int perturb(pguresvt_handle *h)
+{
+    if (h->perturbed || !h->p.optimize_pgure)
+        return PGS_OK;
+    int64_t seed = h->p.random_seed;
+    if (seed < 0)
+    { // pgure.hpp:52-55: external entropy; not reproducible by construction
+        std::random_device rd;
+        seed = (int64_t)((((uint64_t)rd() << 32) | rd()) >> 1);
+    }
+    h->seed_used = seed;
+    const long long n = (long long)(h->fsz * h->win);
+    const int chunk = 64;
+    const long long nthreads = (2 * n + chunk - 1) / chunk;
+    k_perturb<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dD1, h->dD2, n, (unsigned long long)seed, h->vP, chunk);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    h->perturbed = true;
+    return PGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-frame stages
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static void launch_window(pguresvt_handle *h, const T *src, double *dst, double vmax)
+{
+    const size_t n = h->fsz * h->win;
+    k_window<T><<<std::min(cdiv(n, 256), h->sm_count * 16), 256, 0, h->st>>>(src, dst, n, vmax);
+    LAUNCHED(h);
+}
+
+static int stage_window(pguresvt_handle *h, uint32_t t)
+{
+    const uint32_t a = window_start(h, t);
+    h->cur_a = a;
+    const uint32_t la = a - h->r0; // local index of the first window frame
+    double uMax = h->xmax[la], wMax = h->zmax[la];
+    for (uint32_t k = 1; k < h->win; k++)
+    {
+        uMax = std::max(uMax, h->xmax[la + k]);
+        wMax = std::max(wMax, h->zmax[la + k]);
+    }
+    h->cur_uMax = uMax;
+    h->cur_wMax = wMax;
+    const size_t off = h->fsz * la;
+    switch (h->dtype)
+    {
+    case PGS_U8:
+        launch_window<uint8_t>(h, (const uint8_t *)h->dX + off, h->dU, uMax);
+        break;
+    case PGS_U16:
+        launch_window<uint16_t>(h, (const uint16_t *)h->dX + off, h->dU, uMax);
+        break;
+    case PGS_F32:
+        launch_window<float>(h, (const float *)h->dX + off, h->dU, uMax);
+        break;
+    default:
+        launch_window<double>(h, (const double *)h->dX + off, h->dU, uMax);
+        break;
+    }
+    if (h->p.motion_estimation)
+    {
+        if (h->p.median_size > 0)
+            launch_window<uint16_t>(h, h->dZ + off, h->dW, wMax);
+        else
+            switch (h->dtype)
+            {
+            case PGS_U8:
+                launch_window<uint8_t>(h, (const uint8_t *)h->dX + off, h->dW, wMax);
+                break;
+            case PGS_U16:
+                launch_window<uint16_t>(h, (const uint16_t *)h->dX + off, h->dW, wMax);
+                break;
+            case PGS_F32:
+                launch_window<float>(h, (const float *)h->dX + off, h->dW, wMax);
+                break;
+            default:
+                launch_window<double>(h, (const double *)h->dX + off, h->dW, wMax);
+                break;
+            }
+    }
+    // reference slice of the trajectories (arps.hpp:54-113) and output slice (pguresvt.hpp:155-166)
+    if (t < h->fw)
+    {
+        h->cur_ref = (int)t;
+        h->cur_sl = (int)t;
+    }
+    else if (t >= h->nframes - h->fw)
+    {
+        h->cur_ref = (int)(t - (h->nframes - h->win)); // arps.hpp:82 with Nt = A.n_slices
+        h->cur_sl = (int)(t - (h->nframes - h->Nt));   // pguresvt.hpp:161 with the driver's Nt
+    }
+    else
+    {
+        h->cur_ref = (int)h->fw;
+        h->cur_sl = (int)h->fw;
+    }
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+static void arps_pair(pguresvt_handle *h, int f1, int f2, int f3)
+{
+    const double oobs2 = 1.0 / (double)(h->p.block_size * h->p.block_size);
+    k_arps_pair<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.block_size, h->p.motion_window, f1, f2, f3,
+                                                          h->dPos, h->dMot, h->vecSize, oobs2, h->dNcost);
+    LAUNCHED(h);
+}
+
+static int stage_motion(pguresvt_handle *h, uint32_t t) // MotionEstimator::Estimate, arps.hpp:52-134
+{
+    const int tw = (int)h->fw, Ntw = (int)h->win, nImages = (int)h->nframes, ti = (int)t;
+    CU(cudaMemsetAsync(h->dPos, 0, (size_t)h->win * h->vecSize * sizeof(short2), h->st));
+    CU(cudaMemsetAsync(h->dMot, 0, (size_t)h->win * h->vecSize * sizeof(short2), h->st));
+    CU(cudaMemsetAsync(h->dNcost, 0, sizeof(unsigned long long), h->st));
+    k_seed_pos<<<cdiv(h->vecSize, 256), 256, 0, h->st>>>(h->dPos, h->vecSize, h->M1, h->cur_ref);
+    LAUNCHED(h);
+    if (h->p.motion_estimation)
+    {
+        if (ti < tw)
+        {
+            const int loopEnd = Ntw - ti - 1;
+            for (int i = 0; i < loopEnd; i++)
+                arps_pair(h, ti + i, ti + i + 1, ti + i);
+            for (int i = 0; i < ti; i++)
+            {
+                const int negInc = -1 * (i + 1);
+                arps_pair(h, ti + negInc + 1, ti + negInc, ti + negInc + 1);
+            }
+        }
+        else if (ti >= nImages - tw)
+        {
+            const int endFrame = ti - (nImages - Ntw);
+            const int loopEnd = 2 * tw - endFrame;
+            for (int i = 0; i < loopEnd; i++)
+                arps_pair(h, endFrame + i, endFrame + i + 1, endFrame + i);
+            for (int i = 0; i < endFrame; i++)
+            {
+                const int negInc = -1 * (i + 1);
+                if (2 * tw == endFrame)
+                    arps_pair(h, endFrame + negInc + 1, endFrame + negInc, endFrame + negInc);
+                else
+                    arps_pair(h, endFrame + negInc + 1, endFrame + negInc, endFrame + negInc + 1);
+            }
+        }
+        else
+        {
+            for (int i = 0; i < tw; i++)
+                arps_pair(h, tw + i, tw + i + 1, tw + i);
+            for (int i = 0; i < tw; i++)
+            {
+                const int negInc = -1 * (i + 1);
+                arps_pair(h, tw + negInc + 1, tw + negInc, tw + negInc + 1);
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-118 (+ pgure.hpp:80-82)
+{
+    Perturb pt;
+    pt.d1 = h->dD1;
+    pt.d2neg = h->dD2;
+    pt.mode = obj;
+    const double eps1 = 1.0 * 0.0001; // U.max() * 1e-4 with U max-normalised (pgure.hpp:72)
+    pt.eps = (obj == 1) ? eps1 : 100 * eps1;
+    pt.dNeg = h->d2Neg;
+    pt.dPos = h->d2Pos;
+    const int max_sweeps = 30;
+    const double tol = 1e-15, tol2 = tol * tol;
+    if (h->use_reg_svd)
+    {
+        const long long nthreads = (long long)h->P * 8;
+        k_svd_16x15<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
+                                                            max_sweeps, tol2, h->dSweeps);
+    }
+    else
+    {
+        const size_t per_warp = ((size_t)h->m * h->n + (size_t)h->n * h->n + h->n) * sizeof(double);
+        int wpb = (int)std::min<size_t>(8, (size_t)(96 * 1024) / per_warp);
+        if (wpb < 1)
+            wpb = 1;
+        const size_t smem = per_warp * wpb;
+        if (smem > 200 * 1024)
+            return fail(PGS_ERR_UNSUPPORTED, "Casorati matrix %dx%d too large for the shared-memory SVD kernel", h->m, h->n);
+        if (smem > 48 * 1024)
+            CU(cudaFuncSetAttribute(k_svd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_svd_smem<<<cdiv(h->P, wpb), wpb * 32, smem, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N,
+                                                               h->p.block_size, h->n, h->ldv, h->dFac[obj], h->rec, max_sweeps,
+                                                               tol2, h->dSweeps);
+    }
+    LAUNCHED(h);
+    h->stats[1] += h->P;
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+static int stage_count(pguresvt_handle *h, int only_k)
+{
+    const size_t wtot = h->fsz * h->win;
+    if (only_k >= 0)
+        CU(cudaMemsetAsync(h->dCnt + h->fsz * only_k, 0, h->fsz * sizeof(unsigned), h->st));
+    else
+        CU(cudaMemsetAsync(h->dCnt, 0, wtot * sizeof(unsigned), h->st));
+    const long long nt = (long long)h->P * (only_k >= 0 ? 1 : h->win);
+    k_count<<<cdiv(nt, 256), 256, 0, h->st>>>(h->dPos, h->dIds, h->P, h->vecSize, h->N, h->p.block_size, h->win, only_k,
+                                              h->dCnt);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) // SVT::Reconstruct, svt.hpp:121-160
+{
+    const size_t wtot = h->fsz * h->win;
+    if (only_k >= 0)
+        CU(cudaMemsetAsync(h->dAcc[obj] + h->fsz * only_k, 0, h->fsz * sizeof(double), h->st));
+    else
+        CU(cudaMemsetAsync(h->dAcc[obj], 0, wtot * sizeof(double), h->st));
+    const int G = (h->m <= 16) ? 16 : 32;
+    const int threads = 128, gpb = threads / G;
+    const int NMAX = (h->n <= 16) ? 16 : 32;
+    const size_t smem = ((size_t)h->ldv * h->n + 2 * NMAX) * sizeof(double) * gpb;
+    if (NMAX == 16)
+        k_recon<16><<<cdiv(h->P, gpb), threads, smem, h->st>>>(h->dFac[obj], h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos,
+                                                                h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
+                                                                only_k, h->dAcc[obj], G);
+    else
+        k_recon<32><<<cdiv(h->P, gpb), threads, smem, h->st>>>(h->dFac[obj], h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos,
+                                                                h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
+                                                                only_k, h->dAcc[obj], G);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+// One evaluation of PGURE::CalculatePGURE (pgure.hpp:120-137).  (alpha, mu, sigma) are the PGURE object's
+// members, i.e. AFTER the sigma/mu swap of pguresvt.hpp:133.
+static int objective(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
+{
+    for (int k = 0; k < h->nobj; k++)
+    {
+        int rc = launch_recon(h, h->objs[k], lambda, -1);
+        if (rc)
+            return rc;
+    }
+    const size_t wtot = h->fsz * h->win;
+    const double sigmasq = sigma * sigma;
+    k_risk<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dD1, h->dD2, h->dCnt, h->dAcc[0], h->dAcc[1], h->dAcc[2], h->dAcc[3], wtot,
+                                           alpha, mu, sigmasq, h->d2Neg, h->d2Pos, h->dPartial);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 5, h->dOut);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hOut, h->dOut, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const double s1 = h->hOut[0], s2 = h->hOut[1], s3 = h->hOut[2], s4 = h->hOut[3], s5 = h->hOut[4];
+    const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
+    const double OoN = 1.0 / ((double)h->N * h->N * h->win); // pgure.hpp:49 with Nt = U.n_slices
+    *value = OoN * (s1 - (alpha + mu) * s2 + (2 / eps1 * s3) - (2 * sigmasq * alpha / (eps2 * eps2) * s4) + (2 * mu * s5) + mu) -
+             sigmasq;
+    if (terms)
+        for (int q = 0; q < 5; q++)
+            terms[q] = h->hOut[q];
+    h->stats[2] += 1;
+    return PGS_OK;
+}
+
+static int sum_u(pguresvt_handle *h, double *out)
+{
+    const size_t wtot = h->fsz * h->win;
+    k_sum<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, wtot, h->dPartial);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 1, h->dOut);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hOut, h->dOut, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    *out = h->hOut[0];
+    return PGS_OK;
+}
+
+struct StageTimer
+{
+    pguresvt_handle *h;
+    int slot;
+    StageTimer(pguresvt_handle *h_, int slot_) : h(h_), slot(slot_) { cudaEventRecord(h->ev[0], h->st); }
+    ~StageTimer()
+    {
+        cudaEventRecord(h->ev[1], h->st);
+        cudaEventSynchronize(h->ev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        h->stats[slot] += ms;
+    }
+};
+
+// window + trajectories + SVD factors (+ weights for the lambda search) of frame t, cached per handle
+static int prepare_frame(pguresvt_handle *h, uint32_t t)
+{
+    int rc;
+    if ((rc = prefilter(h)))
+        return rc;
+    if ((rc = perturb(h)))
+        return rc;
+    if (h->cur_t == (long long)t)
+        return PGS_OK;
+    h->cur_t = -1;
+    if ((rc = stage_window(h, t)))
+        return rc;
+    {
+        StageTimer tm(h, 4);
+        if ((rc = stage_motion(h, t)))
+            return rc;
+    }
+    {
+        StageTimer tm(h, 5);
+        CU(cudaMemsetAsync(h->dSweeps, 0, sizeof(int), h->st));
+        for (int k = 0; k < h->nobj; k++)
+            if ((rc = stage_svd(h, h->objs[k])))
+                return rc;
+        int sw = 0;
+        CU(cudaMemcpyAsync(&sw, h->dSweeps, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        h->stats[10] = std::max(h->stats[10], (double)sw);
+    }
+    if (h->p.optimize_pgure)
+    {
+        if ((rc = stage_count(h, -1)))
+            return rc;
+        if ((rc = sum_u(h, &h->cur_sumU)))
+            return rc;
+    }
+    h->cur_t = t;
+    return PGS_OK;
+}
+
+static int estimate_noise(pguresvt_handle *h, double &alpha, double &mu, double &sigma)
+{
+    // Q9: the reference runs the estimator even when all three are user-supplied and then discards the
+    // result; skipping it in that case is bit-identical.
+    if (alpha >= 0. && mu >= 0. && sigma >= 0.)
+        return PGS_OK;
+    StageTimer tm(h, 8);
+    return noise_estimate_window(h->noise_ws, h->dU, (int)h->N, (int)h->win, (int)h->p.noise_method, h->sm_count, h->st, alpha, mu,
+                                 sigma, &h->launches, g_err);
+}
+
+static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.hpp:90-167
+{
+    int rc;
+    if ((rc = prepare_frame(h, t)))
+        return rc;
+    const pguresvt_params &p = h->p;
+    double lambda = (p.lambda_est >= 0.0) ? p.lambda_est : -1.0;
+    double alpha = (p.alpha_est >= 0.0) ? p.alpha_est : -1.0;
+    double mu = (p.mu_est >= 0.0) ? p.mu_est : -1.0;
+    double sigma = (p.sigma_est >= 0.0) ? p.sigma_est : -1.0;
+    if (p.optimize_pgure)
+    {
+        if ((rc = estimate_noise(h, alpha, mu, sigma)))
+            return rc;
+        StageTimer tm(h, 6);
+        const double OoNxNyNt = 1.0 / ((double)h->N * h->N * h->Nt); // pguresvt.hpp:60 (the driver's Nt)
+        double start = (lambda >= 0.0) ? lambda : h->cur_sumU * OoNxNyNt;
+        start = std::max(0.0, start);
+        const double ub = std::max(100.0, start);
+        Sbplx1D opt;
+        opt.lb = 0.0;
+        opt.ub = ub;
+        opt.ftol_rel = p.tol;
+        opt.xtol_abs = 1E-12;
+        opt.maxeval = (int)p.max_iter;
+        double last = start;
+        int err = PGS_OK;
+        // NB the PGURE object receives (alpha, sigma, mu) for its (alpha, mu, sigma) — SURVEY Q1
+        auto f = [&](double x) -> double {
+            double v = 0;
+            last = x;
+            const int e = objective(h, x, alpha, sigma, mu, &v, nullptr);
+            if (e && !err)
+                err = e;
+            return v;
+        };
+        const int st = opt.minimize(f, start, std::sqrt(start));
+        if (err)
+            return err;
+        if (st == SBPLX_INVALID_ARGS)
+            return fail(PGS_ERR_OPT,
+                        "lambda search cannot start from %g (zero initial step; the reference's NLopt call throws here)", start);
+        lambda = last; // the LAST evaluated lambda, not the optimum (pgure.hpp:128,236)
+    }
+    {
+        StageTimer tm(h, 7);
+        if (!p.optimize_pgure)
+            if ((rc = stage_count(h, h->cur_sl)))
+                return rc;
+        if ((rc = launch_recon(h, 0, lambda, h->cur_sl)))
+            return rc;
+        const uint32_t lt = t - h->fb;
+        k_finalize<<<std::min(cdiv(h->fsz, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dCnt, h->fsz * h->cur_sl, h->fsz,
+                                                                                    h->cur_uMax, h->dY + h->fsz * lt);
+        LAUNCHED(h);
+        const uint32_t nblk = h->fe - h->fb;
+        h->est[lt + (size_t)nblk * 0] = lambda;
+        h->est[lt + (size_t)nblk * 1] = alpha;
+        h->est[lt + (size_t)nblk * 2] = mu;
+        h->est[lt + (size_t)nblk * 3] = sigma;
+    }
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_process(pguresvt_handle *h)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    g_err.clear();
+    CU(cudaSetDevice(h->p.device));
+    if (!h->uploaded)
+        return fail(PGS_ERR_ARG, "pguresvt_process: no input uploaded");
+    for (int i = 0; i < PGS_NSTATS; i++)
+        h->stats[i] = 0;
+    h->launches = 0;
+    h->prefiltered = false;
+    h->cur_t = -1;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->st));
+    int rc;
+    {
+        StageTimer tm(h, 3);
+        if ((rc = prefilter(h)))
+            return rc;
+    }
+    for (uint32_t t = h->fb; t < h->fe; t++)
+        if ((rc = process_frame(h, t)))
+            return rc;
+    CU(cudaMemcpyAsync(h->dEst, h->est.data(), h->est.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->stats[9] = ms;
+    h->stats[0] = (double)h->launches;
+    h->stats[11] = (double)(h->rec * (size_t)h->P * sizeof(double) * h->nobj);
+    return PGS_OK;
+}
+
+extern "C" double *pguresvt_device_output(pguresvt_handle *h) { return h ? h->dY : nullptr; }
+extern "C" double *pguresvt_device_estimates(pguresvt_handle *h) { return h ? h->dEst : nullptr; }
+
+extern "C" int pguresvt_download(pguresvt_handle *h, double *Y_full, double *estimates_full)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->p.device));
+    const uint32_t nblk = h->fe - h->fb;
+    if (Y_full)
+        CU(cudaMemcpyAsync(Y_full + h->fsz * h->fb, h->dY, h->fsz * nblk * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (estimates_full) // (n_frames, 4) column-major
+        for (int q = 0; q < 4; q++)
+            for (uint32_t i = 0; i < nblk; i++)
+                estimates_full[(h->fb + i) + (size_t)h->nframes * q] = h->est[i + (size_t)nblk * q];
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_get_stats(const pguresvt_handle *h, double *stats)
+{
+    if (!h || !stats)
+        return fail(PGS_ERR_ARG, "null argument");
+    for (int i = 0; i < PGS_NSTATS; i++)
+        stats[i] = h->stats[i];
+    return PGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one-shot entry points
+// ------------------------------------------------------------------------------------------------------
+static int run_any(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, const pguresvt_params *p,
+                   double *Y, double *estimates)
+{
+    if (!X || !Y || !estimates || !p)
+        return fail(PGS_ERR_ARG, "null argument");
+    pguresvt_handle *h = pguresvt_create(dtype, n_rows, n_cols, n_frames, p, 0, n_frames);
+    if (!h)
+        return g_err.find("CUDA") != std::string::npos ? PGS_ERR_CUDA : PGS_ERR_ARG;
+    int rc = pguresvt_upload(h, X);
+    if (!rc)
+        rc = pguresvt_process(h);
+    if (!rc)
+        rc = pguresvt_download(h, Y, estimates);
+    const std::string keep = g_err;
+    pguresvt_destroy(h);
+    g_err = keep;
+    return rc;
+}
+extern "C" int pguresvt_run_u8(const uint8_t *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y, double *e)
+{
+    return run_any(PGS_U8, X, r, c, f, p, Y, e);
+}
+extern "C" int pguresvt_run_u16(const uint16_t *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y,
+                                double *e)
+{
+    return run_any(PGS_U16, X, r, c, f, p, Y, e);
+}
+extern "C" int pguresvt_run_f32(const float *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y, double *e)
+{
+    return run_any(PGS_F32, X, r, c, f, p, Y, e);
+}
+extern "C" int pguresvt_run_f64(const double *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y, double *e)
+{
+    return run_any(PGS_F64, X, r, c, f, p, Y, e);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// stage probes
+// ------------------------------------------------------------------------------------------------------
+#define CHECK_T(h, t)                                                                        \
+    if (!(h))                                                                                \
+        return fail(PGS_ERR_ARG, "null handle");                                             \
+    if ((t) < (h)->fb || (t) >= (h)->fe)                                                     \
+        return fail(PGS_ERR_ARG, "frame %u outside the handle's block [%u,%u)", (t), (h)->fb, (h)->fe); \
+    CU(cudaSetDevice((h)->p.device));
+
+extern "C" int pguresvt_probe_median(pguresvt_handle *h, uint32_t t, uint16_t *Z)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    if (t < h->r0 || t >= h->r1)
+        return fail(PGS_ERR_ARG, "frame %u not resident", t);
+    if (h->p.median_size <= 0)
+        return fail(PGS_ERR_ARG, "median prefilter is disabled");
+    CU(cudaSetDevice(h->p.device));
+    int rc = prefilter(h);
+    if (rc)
+        return rc;
+    CU(cudaMemcpy(Z, h->dZ + h->fsz * (t - h->r0), h->fsz * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_arps(pguresvt_handle *h, uint32_t t, int32_t *patches)
+{
+    CHECK_T(h, t);
+    int rc = prepare_frame(h, t);
+    if (rc)
+        return rc;
+    std::vector<short2> hp((size_t)h->win * h->vecSize);
+    CU(cudaMemcpy(hp.data(), h->dPos, hp.size() * sizeof(short2), cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < h->win; k++)
+        for (int it = 0; it < h->vecSize; it++)
+        {
+            const short2 q = hp[(size_t)k * h->vecSize + it];
+            patches[0 + 2 * ((size_t)it + (size_t)h->vecSize * k)] = q.x;
+            patches[1 + 2 * ((size_t)it + (size_t)h->vecSize * k)] = q.y;
+        }
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_singular_values(pguresvt_handle *h, uint32_t t, int obj, double *S, int64_t *n_patches)
+{
+    CHECK_T(h, t);
+    if (obj < 0 || obj > 3 || !h->dFac[obj])
+        return fail(PGS_ERR_ARG, "SVT object %d not present in this configuration", obj);
+    int rc = prepare_frame(h, t);
+    if (rc)
+        return rc;
+    if (n_patches)
+        *n_patches = h->P;
+    if (S)
+    {
+        const size_t soff = (size_t)h->m * h->n + (size_t)h->ldv * h->n;
+        CU(cudaMemcpy2D(S, (size_t)h->n * sizeof(double), h->dFac[obj] + soff, h->rec * sizeof(double), (size_t)h->n * sizeof(double),
+                        h->P, cudaMemcpyDeviceToHost));
+    }
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_pgure(pguresvt_handle *h, uint32_t t, double alpha, double mu, double sigma, int n,
+                                    const double *lambdas, double *values, double *terms)
+{
+    CHECK_T(h, t);
+    if (!h->p.optimize_pgure)
+        return fail(PGS_ERR_ARG, "handle was created with optimize_pgure = false");
+    int rc = prepare_frame(h, t);
+    if (rc)
+        return rc;
+    for (int i = 0; i < n; i++)
+        if ((rc = objective(h, lambdas[i], alpha, sigma, mu, &values[i], terms ? terms + 5 * i : nullptr)))
+            return rc;
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_reconstruct(pguresvt_handle *h, uint32_t t, double lambda, double *v)
+{
+    CHECK_T(h, t);
+    int rc = prepare_frame(h, t);
+    if (rc)
+        return rc;
+    const size_t wtot = h->fsz * h->win;
+    if (!h->p.optimize_pgure)
+        if ((rc = stage_count(h, -1)))
+            return rc;
+    if ((rc = launch_recon(h, 0, lambda, -1)))
+        return rc;
+    if (!h->dV)
+        CU(cudaMalloc(&h->dV, wtot * sizeof(double)));
+    k_finalize<<<std::min(cdiv(wtot, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dCnt, 0, wtot, 1.0, h->dV);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(v, h->dV, wtot * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_perturbations(pguresvt_handle *h, int8_t *delta1, int8_t *delta2neg)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    if (!h->p.optimize_pgure)
+        return fail(PGS_ERR_ARG, "handle was created with optimize_pgure = false");
+    CU(cudaSetDevice(h->p.device));
+    int rc = perturb(h);
+    if (rc)
+        return rc;
+    const size_t wtot = h->fsz * h->win;
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaMemcpy(delta1, h->dD1, wtot, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(delta2neg, h->dD2, wtot, cudaMemcpyDeviceToHost));
+    return PGS_OK;
+}
+
+extern "C" int pguresvt_probe_noise(pguresvt_handle *h, uint32_t t, double *alpha, double *mu, double *sigma)
+{
+    CHECK_T(h, t);
+    int rc = prefilter(h);
+    if (rc)
+        return rc;
+    h->cur_t = -1;
+    if ((rc = stage_window(h, t)))
+        return rc;
+    return noise_estimate_window(h->noise_ws, h->dU, (int)h->N, (int)h->win, (int)h->p.noise_method, h->sm_count, h->st, *alpha, *mu,
+                                 *sigma, &h->launches, g_err);
+}
+
+extern "C" int pguresvt_device_info(int device, char *name, int len)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    {
+        fail(PGS_ERR_CUDA, "no CUDA device %d", device);
+        return -1;
+    }
+    if (name && len > 0)
+    {
+        strncpy(name, prop.name, (size_t)len - 1);
+        name[len - 1] = 0;
+    }
+    return prop.multiProcessorCount;
+}
+
+// Host optimiser exposed for the CPU-only tests (the same object the lambda search uses).
+extern "C" int pguresvt_host_sbplx(double (*f)(double, void *), void *data, double x0, double lb, double ub, double step,
+                                   double ftol_rel, double xtol_abs, int maxeval, double *xbest, double *fbest, int *nevals)
+{
+    Sbplx1D opt;
+    opt.lb = lb;
+    opt.ub = ub;
+    opt.ftol_rel = ftol_rel;
+    opt.xtol_abs = xtol_abs;
+    opt.maxeval = maxeval;
+    auto fn = [&](double x) { return f(x, data); };
+    const int st = opt.minimize(fn, x0, step);
+    if (xbest)
+        *xbest = opt.xbest;
+    if (fbest)
+        *fbest = opt.fbest;
+    if (nevals)
+        *nevals = opt.nevals;
+    return st;
+}
+
+// number of patches and the sorted patch-id set of SVT::Decompose (svt.hpp:61-97) — host logic, no GPU needed
+extern "C" int64_t pguresvt_host_patch_ids(uint32_t N, uint32_t bs, uint32_t bo, int32_t *out, int64_t cap)
+{
+    std::vector<int> ids = patch_ids((int)N, (int)bs, (int)bo);
+    if (out)
+        for (int64_t i = 0; i < (int64_t)ids.size() && i < cap; i++)
+            out[i] = ids[i];
+    return (int64_t)ids.size();
+}
+
+#include "hotpixel.cuh"
+extern "C" int pguresvt_hotpixel_u16(uint16_t *seq, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, double threshold,
+                                     int device)
+{
+    if (!seq)
+        return fail(PGS_ERR_ARG, "null argument");
+    return hotpixel_filter_u16(seq, n_rows, n_cols, n_frames, threshold, device, g_err);
+}

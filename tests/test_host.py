@@ -1,0 +1,156 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/*.h
+declares, host logic (patch-id set, 1-D subplex) agrees with the oracle, and the Python mirror keeps the
+reference's argument checks (pguresvt/tests/test_svt.py:109-164).  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import orc
+from pguresvt import SVT, mixed_noise_model
+from pguresvt import _pguresvt as bridge
+
+
+def test_abi_exports_every_declared_symbol():
+    L = bridge.load()
+    hdr = open(os.path.join(ROOT, "include", "pguresvt_b200.h")).read()
+    names = set(re.findall(r"\b(pguresvt_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"pguresvt_params", "pguresvt_handle"}
+    assert len(names) >= 26
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+
+
+def test_params_struct_layout_matches_header():
+    # 4*u32, i64, 2*u32, 2*i64, 3*i32 (+pad), 5*f64, 4*i32
+    assert C.sizeof(bridge.Params) == 16 + 8 + 8 + 16 + 16 + 40 + 16
+    assert bridge.Params.lambda_est.offset == 64
+
+
+def test_no_gpu_fails_loudly_or_creates():
+    L = bridge.load()
+    p = bridge.make_params()
+    h = L.pguresvt_create(1, 32, 32, 16, C.byref(p), 0, 16)
+    if not h:
+        assert "CUDA" in bridge.last_error()
+    else:
+        L.pguresvt_destroy(h)
+    # argument errors are reported, not thrown
+    assert not L.pguresvt_create(1, 32, 48, 16, C.byref(p), 0, 16)
+    assert "square" in bridge.last_error()
+
+
+@pytest.mark.parametrize("cfg", [(32, 4, 1), (32, 4, 2), (128, 16, 2), (256, 4, 2), (32, 4, 3), (64, 8, 3)])
+def test_patch_ids_match_oracle(cfg):
+    N, bs, bo = cfg
+    L = bridge.load()
+    n = L.pguresvt_host_patch_ids(N, bs, bo, None, 0)
+    out = np.zeros(n, dtype=np.int32)
+    L.pguresvt_host_patch_ids(N, bs, bo, out.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    s = orc.SVTObj(np.zeros((2, (N - bs + 1) ** 2, 3), dtype=np.int64), N, 3, bs, bo, True)
+    assert np.array_equal(out, s.patch_ids())
+
+
+_OBJ = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
+
+def _host_sbplx(f, x0, lb, ub, step, ftol=1e-7, xtol=1e-12, maxeval=500):
+    trace = []
+
+    def g(x, _):
+        v = float(f(x))
+        trace.append((x, v))
+        return v
+
+    cb = _OBJ(g)
+    L = bridge.load()
+    L.pguresvt_host_sbplx.restype = C.c_int
+    xb, fb, ne = C.c_double(0), C.c_double(0), C.c_int(0)
+    st = L.pguresvt_host_sbplx(cb, None, C.c_double(x0), C.c_double(lb), C.c_double(ub), C.c_double(step),
+                               C.c_double(ftol), C.c_double(xtol), C.c_int(maxeval), C.byref(xb), C.byref(fb), C.byref(ne))
+    return dict(x=xb.value, minf=fb.value, nevals=ne.value, status=st, trace=trace)
+
+
+@pytest.mark.parametrize("fn", [
+    lambda x: (x - 0.3) ** 2 + 1.0,
+    lambda x: 3.0 * x - 100.0,
+    lambda x: -x,
+    lambda x: np.cos(3 * x) + 0.1 * x,
+    lambda x: 0.0045 + 1e-6 * (np.log1p(x) - 3.4) ** 2,
+    lambda x: abs(x - 50.0),
+])
+@pytest.mark.parametrize("x0", [0.05, 5.0, 99.0])
+def test_host_sbplx_follows_oracle_sequence(fn, x0):
+    """The product's optimiser and the oracle's restatement of NLopt SBPLX probe the same points in the same
+    order (lambda parity is path dependent: SURVEY H1)."""
+    a = _host_sbplx(fn, x0, 0.0, 100.0, np.sqrt(x0))
+    b = orc.sbplx_1d(fn, x0, 0.0, 100.0, np.sqrt(x0))
+    assert a["status"] == b["status"] and a["nevals"] == b["nevals"]
+    assert a["trace"] == b["trace"]
+    assert a["x"] == b["x"] and a["minf"] == b["minf"]
+
+
+def test_host_sbplx_maxeval_and_invalid():
+    a = _host_sbplx(lambda x: (x - 3) ** 2, 1.0, 0.0, 100.0, 1.0, maxeval=7)
+    b = orc.sbplx_1d(lambda x: (x - 3) ** 2, 1.0, 0.0, 100.0, 1.0, maxeval=7)
+    assert a["status"] == b["status"] == 5 and a["nevals"] == b["nevals"] == 7 and a["trace"] == b["trace"]
+    assert _host_sbplx(lambda x: x, 0.0, 0.0, 100.0, 0.0)["status"] == -2
+
+
+# ---- the reference's TestErrors, verbatim in behaviour (test_svt.py:109-164) ----
+class TestErrors:
+    def setup_method(self, method):
+        self.X = np.ones((32, 32, 16))
+
+    def test_negative(self):
+        with pytest.raises(ValueError, match="Negative values found in data"):
+            SVT().denoise(-1 * self.X)
+
+    def test_overlap(self):
+        with pytest.raises(ValueError, match="Invalid patch_overlap parameter"):
+            SVT(patch_size=4, patch_overlap=5).denoise(self.X)
+
+    @pytest.mark.parametrize("tl", [0, 2, -1])
+    def test_trajectory(self, tl):
+        with pytest.raises(ValueError, match="Invalid trajectory_length parameter"):
+            SVT(trajectory_length=tl).denoise(self.X)
+
+    @pytest.mark.parametrize("mw", [1, 4])
+    def test_motion_window(self, mw):
+        with pytest.raises(ValueError, match="Invalid motion_window parameter"):
+            SVT(motion_window=mw).denoise(self.X)
+
+    def test_motion_filter(self):
+        with pytest.raises(ValueError, match="Invalid motion_filter parameter"):
+            SVT(motion_filter=1.5).denoise(self.X)
+
+    @pytest.mark.parametrize("lam", [None, -1.0])
+    def test_lambda(self, lam):
+        with pytest.raises(ValueError, match="Invalid lambda1 parameter"):
+            SVT(optimize_pgure=False, lambda1=lam).denoise(self.X)
+
+    def test_square(self):
+        with pytest.raises(ValueError, match="requires square images"):
+            SVT().denoise(np.ones((32, 64, 16)))
+
+    def test_power_of_two(self):
+        with pytest.raises(ValueError, match="requires image dimensions 2"):
+            SVT().denoise(np.ones((48, 48, 16)))
+
+    def test_dtype(self):
+        with pytest.raises(TypeError, match="Invalid dtype"):
+            SVT(optimize_pgure=False, lambda1=1.0).denoise(self.X.astype(np.int32))
+
+
+def test_mixed_noise_model_errors_and_seeds():
+    X = np.random.RandomState(0).uniform(0, 255, size=(8, 8, 4))
+    with pytest.raises(ValueError, match="alpha should be in range"):
+        mixed_noise_model(X, alpha=-1.0)
+    with pytest.raises(ValueError, match="sigma should be"):
+        mixed_noise_model(X, sigma=-1.0)
+    for rs in (None, 101, np.random.RandomState(101)):
+        assert mixed_noise_model(X, random_state=rs).shape == X.shape
+    assert np.array_equal(mixed_noise_model(X, random_state=5), mixed_noise_model(X, random_state=5))
