@@ -33,6 +33,13 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
+// v / weights with non-finite -> 0 (svt.hpp:163-164)
+__device__ __forceinline__ double norm_or_zero(double a, unsigned c)
+{
+    const double v = a / (double)c;
+    return isfinite(v) ? v : 0.0;
+}
+
 template <typename T>
 __device__ __forceinline__ double to_double(T v)
 {
@@ -749,6 +756,487 @@ __global__ void __launch_bounds__(128)
         atomicMax(sweeps_out, sweep);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// K_svd (register, v2) — 16x15 Casorati matrices, FOUR lanes per matrix (eight matrices per warp).
+// Lane j of a group owns patch column j, i.e. rows 4j..4j+3 of A (16 x 16 with a zero 16th column), in
+// registers; V is NOT accumulated during the sweeps.  Per round of the round-robin ordering:
+//   * 24 partial dot products over the lane's four rows,
+//   * one transposing butterfly over the 4 lanes (6 shuffles per quantity) leaving lane j with the sums of slot
+//     pairs 2j and 2j+1, for which it derives the two rotations with approximate-reciprocal/rsqrt + Newton
+//     (no IEEE divide/sqrt slow paths),
+//   * (c, s) broadcast, rotations applied to the lane's rows, columns moved along the round-robin cycle.
+// A sweep in which no pair had |cos| > 1e-6 is the last one (quadratic convergence puts every pair below
+// ~1e-12 afterwards), so no extra "check" sweep is spent.
+// WARM = 1 pre-multiplies the gathered matrix by the V of SVT object 0 (the unperturbed data): the perturbed
+// matrices U +- eps2*delta2 then start with nearly orthogonal columns and converge in about half the sweeps.
+// After convergence  U = W / sigma  (W = A V = rotated columns) is written, and  V = A^T U / sigma  is rebuilt
+// from the re-gathered A — accurate in the product f(sigma_k) u_k v_k^T that SVT consumes, because the soft
+// threshold gives f(sigma_k) <= sigma_k.  Singular values are stored in slot (column) order with
+// S[15] = sigma_max; U, V column-major with leading dimension 16.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+}
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = r * fma(-hx * r, r, 1.5);
+    r = r * fma(-hx * r, r, 1.5);
+    return r;
+}
+// rotation for a slot pair with squared norms A, B and inner product G; flags: rotate if cos^2 > tol2,
+// `big` if cos^2 > big2
+__device__ __forceinline__ void jacobi_cs_fast(double A, double B, double G, double tol2, double big2, double &c, double &s,
+                                               bool &big)
+{
+    const double g2 = G * G, ab = A * B;
+    const bool rot = g2 > tol2 * ab;
+    big = big || (g2 > big2 * ab);
+    const double d = B - A;
+    const double q = fma(d, d, 4.0 * g2);
+    const double h = q * rsqrt_fast(q); // sqrt(d^2 + 4 G^2)
+    const double t = ((d >= 0.0) ? 2.0 * G : -2.0 * G) * rcp_fast(fabs(d) + h);
+    const double cc = rsqrt_fast(fma(t, t, 1.0));
+    c = rot ? cc : 1.0;
+    s = rot ? cc * t : 0.0;
+}
+
+// transposing reduction of 8 values over the 4 lanes of a group: lane `sub` gets the sums of x[2*sub], x[2*sub+1]
+__device__ __forceinline__ void tr4_8(const double (&x)[8], int sub, double &o0, double &o1)
+{
+    double y[4];
+    const bool h2 = (sub & 2) != 0, h1 = (sub & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const double send = h2 ? x[j] : x[j + 4];
+        const double keep = h2 ? x[j + 4] : x[j];
+        y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+        const double send0 = h1 ? y[0] : y[2], send1 = h1 ? y[1] : y[3];
+        const double keep0 = h1 ? y[2] : y[0], keep1 = h1 ? y[3] : y[1];
+        o0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
+        o1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
+    }
+}
+// same for 16 values: lane `sub` gets the sums of x[4*sub .. 4*sub+3]
+__device__ __forceinline__ void tr4_16(const double (&x)[16], int sub, double (&o)[4])
+{
+    double y[8];
+    const bool h2 = (sub & 2) != 0, h1 = (sub & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        const double send = h2 ? x[j] : x[j + 8];
+        const double keep = h2 ? x[j + 8] : x[j];
+        y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const double send = h1 ? y[j] : y[j + 4];
+        const double keep = h1 ? y[j + 4] : y[j];
+        o[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+}
+
+template <int WARM>
+__global__ void __launch_bounds__(128, 2)
+    k_svd16_l4(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
+               int vecSize, int N, double *__restrict__ fac, const double *__restrict__ fac0, int max_sweeps, double tol2,
+               double big2, int *__restrict__ sweeps_out)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & 3; // patch column owned by this lane
+    int pidx = gtid >> 2;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const int id = ids[pidx];
+    const size_t fsz = (size_t)N * N;
+
+    double a[4][16];
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * k;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            a[r][k] = load_perturbed(u, vox + r, pt);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        a[r][15] = 0.0;
+
+    if (WARM)
+    { // rows of A times V0 (column-major, ld 16) — each row independently, in place
+        const double *V0 = fac0 + (size_t)SVD16_REC * pidx + SVD16_M * SVD16_N;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            double t[SVD16_N];
+#pragma unroll
+            for (int j = 0; j < SVD16_N; j++)
+            {
+                const double2 *col = reinterpret_cast<const double2 *>(V0 + SVD16_LDV * j);
+                double acc = 0.0;
+#pragma unroll
+                for (int i2 = 0; i2 < 8; i2++)
+                {
+                    const double2 v = col[i2];
+                    acc = fma(a[r][2 * i2], v.x, acc);
+                    if (2 * i2 + 1 < SVD16_N)
+                        acc = fma(a[r][2 * i2 + 1], v.y, acc);
+                }
+                t[j] = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < SVD16_N; j++)
+                a[r][j] = t[j];
+        }
+    }
+
+    int sweep = 0;
+#pragma unroll 1
+    for (; sweep < max_sweeps;)
+    {
+        bool big = false;
+#pragma unroll 1
+        for (int round = 0; round < 15; round++)
+        {
+            double pa[8], pb[8], pg[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                double sa = 0.0, sb = 0.0, sg = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    const double x = a[r][2 * i], y = a[r][2 * i + 1];
+                    sa = fma(x, x, sa);
+                    sb = fma(y, y, sb);
+                    sg = fma(x, y, sg);
+                }
+                pa[i] = sa;
+                pb[i] = sb;
+                pg[i] = sg;
+            }
+            double A0, A1, B0, B1, G0, G1;
+            tr4_8(pa, sub, A0, A1);
+            tr4_8(pb, sub, B0, B1);
+            tr4_8(pg, sub, G0, G1);
+            double c0, s0, c1, s1;
+            jacobi_cs_fast(A0, B0, G0, tol2, big2, c0, s0, big);
+            jacobi_cs_fast(A1, B1, G1, tol2, big2, c1, s1, big);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                const double ci = __shfl_sync(0xffffffffu, (i & 1) ? c1 : c0, i >> 1, 4);
+                const double si = __shfl_sync(0xffffffffu, (i & 1) ? s1 : s0, i >> 1, 4);
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    const double x = a[r][2 * i], y = a[r][2 * i + 1];
+                    a[r][2 * i] = fma(ci, x, -si * y);
+                    a[r][2 * i + 1] = fma(si, x, ci * y);
+                }
+            }
+#define RR_MOVE(X)                 \
+    {                              \
+        const double b0_ = X[1];   \
+        const double t7_ = X[14];  \
+        X[14] = X[12];             \
+        X[12] = X[10];             \
+        X[10] = X[8];              \
+        X[8] = X[6];               \
+        X[6] = X[4];               \
+        X[4] = X[2];               \
+        X[2] = b0_;                \
+        X[1] = X[3];               \
+        X[3] = X[5];               \
+        X[5] = X[7];               \
+        X[7] = X[9];               \
+        X[9] = X[11];              \
+        X[11] = X[13];             \
+        X[13] = X[15];             \
+        X[15] = t7_;               \
+    }
+            RR_MOVE(a[0])
+            RR_MOVE(a[1])
+            RR_MOVE(a[2])
+            RR_MOVE(a[3])
+#undef RR_MOVE
+        }
+        sweep++;
+        if (!__any_sync(0xffffffffu, big))
+            break;
+    }
+
+    // squared column norms: lane `sub` gets columns 4*sub .. 4*sub+3, then everybody gets all 16 sigmas
+    double n2[16], q[4];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+    {
+        double sacc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            sacc = fma(a[r][j], a[r][j], sacc);
+        n2[j] = sacc;
+    }
+    tr4_16(n2, sub, q);
+    double sig[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        sig[j] = __shfl_sync(0xffffffffu, sqrt(q[j & 3]), j >> 2, 4);
+    double smax = 0.0;
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+        smax = fmax(smax, sig[j]);
+
+    double *R = fac + (size_t)SVD16_REC * pidx;
+    // U = W / sigma (columns with sigma below 1e-20 sigma_max carry nothing after thresholding: set to zero);
+    // afterwards a[r][j] holds z = w / sigma^2 for the V rebuild
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+    {
+        const double inv = (sig[j] > smax * 1e-20 && sig[j] > 0.0) ? 1.0 / sig[j] : 0.0;
+        double uu[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            uu[r] = a[r][j] * inv;
+            a[r][j] = uu[r] * inv;
+        }
+        if (valid)
+        {
+            double2 *dst = reinterpret_cast<double2 *>(R + SVD16_M * j + 4 * sub);
+            dst[0] = make_double2(uu[0], uu[1]);
+            dst[1] = make_double2(uu[2], uu[3]);
+        }
+    }
+    if (valid)
+    {
+        double *S = R + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+        // lane `sub` writes S[4*sub .. 4*sub+3]; slot 15 carries sigma_max
+        double2 *dst = reinterpret_cast<double2 *>(S + 4 * sub);
+        dst[0] = make_double2(sig[4 * sub], sig[4 * sub + 1]);
+        dst[1] = make_double2(sig[4 * sub + 2], (sub == 3) ? smax : sig[4 * sub + 3]);
+    }
+    // V(i, k) = sum_rows A(row, i) * z(row, k): loop over i, reduce over the 4 lanes, lane `sub` keeps k = 4*sub..4*sub+3;
+    // four consecutive i are buffered so that each store is 4 contiguous doubles of one column of V
+    double *Vg = R + SVD16_M * SVD16_N;
+#pragma unroll
+    for (int i0 = 0; i0 < 16; i0 += 4)
+    {
+        double vb[4][4]; // [k local][i local]
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++)
+        {
+            const int i = i0 + ii;
+            double part[16];
+            if (i < SVD16_N)
+            {
+                const short2 p = pos[(size_t)i * vecSize + id];
+                const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * i;
+                double ao[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    ao[r] = load_perturbed(u, vox + r, pt);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    double sacc = 0.0;
+                    if (k < SVD16_N)
+                    {
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            sacc = fma(ao[r], a[r][k], sacc);
+                    }
+                    part[k] = sacc;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    part[k] = 0.0;
+            }
+            double o[4];
+            tr4_16(part, sub, o);
+#pragma unroll
+            for (int kl = 0; kl < 4; kl++)
+                vb[kl][ii] = o[kl];
+        }
+        if (valid)
+        {
+#pragma unroll
+            for (int kl = 0; kl < 4; kl++)
+            {
+                const int k = 4 * sub + kl;
+                if (k < SVD16_N)
+                {
+                    double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * k + i0);
+                    dst[0] = make_double2(vb[kl][0], vb[kl][1]);
+                    dst[1] = make_double2(vb[kl][2], vb[kl][3]);
+                }
+            }
+        }
+    }
+    if (sweeps_out && (threadIdx.x & 31) == 0)
+        atomicMax(sweeps_out, sweep);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_eval3 — one PGURE objective evaluation for the 16x15 / reference-eps1 configuration, fused over the
+// three SVT objects (U, U+eps2*delta2, U-eps2*delta2) of every patch (pgure.hpp:130-136, svt.hpp:121-164).
+// Only Uhat enters the risk non-linearly (sum (Uhat-U)^2); U2p and U2m enter through
+//   s4 = sum_voxels delta2 * (U2p - 2 Uhat + U2m) = sum_patches sum_entries (delta2/weights)(voxel) * (b2p - 2 b0 + b2m)
+// so their blocks never need the overlap-add: one group of 16 lanes rebuilds the three 16x15 blocks of a patch
+// (rank-adaptively), adds b0 into the Uhat accumulator (FP64 RED) and folds the second difference straight
+// into a per-block partial sum.  partial: gridDim.x doubles (s4 part).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double soft_f(double s, double smax, double lambda, int expw)
+{
+    const double w = expw ? fabs(smax * exp(-0.5 * lambda * (s * s))) : lambda;
+    return fmax(s - w, 0.0); // s >= 0 from the Jacobi kernels
+}
+
+__global__ void __launch_bounds__(128)
+    k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
+            const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
+            const double *__restrict__ invcnt, const int8_t *__restrict__ d2neg, double dNeg, double dPos,
+            double *__restrict__ acc0, double *__restrict__ partial)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = threadIdx.x & 15; // row of the block owned by this lane; also the slot whose threshold it computes
+    int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const size_t roff = (size_t)SVD16_REC * pidx;
+    const double *R0 = fac0 + roff, *R2 = fac2 + roff, *R3 = fac3 + roff;
+    const int soff = SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+    double f0, f2, f3;
+    {
+        const double sm0 = R0[soff + 15], sm2 = R2[soff + 15], sm3 = R3[soff + 15];
+        f0 = (g < SVD16_N) ? soft_f(R0[soff + g], sm0, lambda, expw) : 0.0;
+        f2 = (g < SVD16_N) ? soft_f(R2[soff + g], sm2, lambda, expw) : 0.0;
+        f3 = (g < SVD16_N) ? soft_f(R3[soff + g], sm3, lambda, expw) : 0.0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, (f0 != 0.0) || (f2 != 0.0) || (f3 != 0.0));
+    m = (m | (m >> 16)) & 0xffffu; // union over the two patches of the warp: uniform trip count
+    double a0[SVD16_N], a2[SVD16_N], a3[SVD16_N];
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+        a0[k] = a2[k] = a3[k] = 0.0;
+    while (m)
+    {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1;
+        const int src = (lane & 16) | kk;
+        const double fk0 = __shfl_sync(0xffffffffu, f0, src);
+        const double fk2 = __shfl_sync(0xffffffffu, f2, src);
+        const double fk3 = __shfl_sync(0xffffffffu, f3, src);
+        const double u0 = R0[SVD16_M * kk + g] * fk0;
+        const double u2 = R2[SVD16_M * kk + g] * fk2;
+        const double u3 = R3[SVD16_M * kk + g] * fk3;
+        const double2 *v0 = reinterpret_cast<const double2 *>(R0 + SVD16_M * SVD16_N + SVD16_LDV * kk);
+        const double2 *v2 = reinterpret_cast<const double2 *>(R2 + SVD16_M * SVD16_N + SVD16_LDV * kk);
+        const double2 *v3 = reinterpret_cast<const double2 *>(R3 + SVD16_M * SVD16_N + SVD16_LDV * kk);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++)
+        {
+            const double2 x0 = v0[k2], x2 = v2[k2], x3 = v3[k2];
+            a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
+            a2[2 * k2] = fma(u2, x2.x, a2[2 * k2]);
+            a3[2 * k2] = fma(u3, x3.x, a3[2 * k2]);
+            if (2 * k2 + 1 < SVD16_N)
+            {
+                a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
+                a2[2 * k2 + 1] = fma(u2, x2.y, a2[2 * k2 + 1]);
+                a3[2 * k2 + 1] = fma(u3, x3.y, a3[2 * k2 + 1]);
+            }
+        }
+    }
+    double s4 = 0.0;
+    if (valid)
+    {
+        const int id = ids[pidx];
+        const size_t fsz = (size_t)N * N;
+        const int r = g & 3, c = g >> 2;
+#pragma unroll
+        for (int k = 0; k < SVD16_N; k++)
+        {
+            const short2 p = pos[(size_t)k * vecSize + id];
+            const size_t vox = (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k;
+            const double ic = invcnt[vox];
+            const double d2 = d2neg[vox] ? dNeg : dPos;
+            s4 = fma(d2 * ic, (a2[k] - 2 * a0[k]) + a3[k], s4);
+            atomicAdd(acc0 + vox, a0[k]);
+        }
+    }
+    s4 = warp_sum(s4);
+    __shared__ double sm[4];
+    if (lane == 0)
+        sm[threadIdx.x >> 5] = s4;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        partial[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+}
+
+// 1 / weights (0 where no patch covers the voxel): svt.hpp:163-164 folded into a multiplier, once per frame
+__global__ void k_invcnt(const unsigned *__restrict__ cnt, size_t n, double *__restrict__ invcnt)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        invcnt[i] = cnt[i] ? 1.0 / (double)cnt[i] : 0.0;
+}
+
+// voxel pass of the fused evaluation: s1 = sum (Uhat - U)^2, s5 = sum Uhat with Uhat = acc0 / weights
+// partial: gridDim.x * 2 doubles
+__global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, const double *__restrict__ acc0,
+                            size_t tot, double *__restrict__ partial)
+{
+    double s1 = 0, s5 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const double v0 = norm_or_zero(acc0[i], cnt[i]);
+        const double d = v0 - u[i];
+        s1 = fma(d, d, s1);
+        s5 += v0;
+    }
+    __shared__ double sm[2][32];
+    s1 = warp_sum(s1);
+    s5 = warp_sum(s5);
+    if ((threadIdx.x & 31) == 0)
+    {
+        sm[0][threadIdx.x >> 5] = s1;
+        sm[1][threadIdx.x >> 5] = s5;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double r1 = (threadIdx.x < (blockDim.x >> 5)) ? sm[0][threadIdx.x] : 0.0;
+        double r5 = (threadIdx.x < (blockDim.x >> 5)) ? sm[1][threadIdx.x] : 0.0;
+        r1 = warp_sum(r1);
+        r5 = warp_sum(r5);
+        if (threadIdx.x == 0)
+        {
+            partial[(size_t)blockIdx.x * 2] = r1;
+            partial[(size_t)blockIdx.x * 2 + 1] = r5;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K_recon — SVT::Reconstruct (svt.hpp:121-160) for one SVT object: threshold the cached singular values
 // (plain lambda, or the exponential weighting of svt.hpp:135-143 with SoftThreshold of utils.hpp:96-106),
@@ -838,11 +1326,6 @@ __global__ void k_recon(const double *__restrict__ fac, size_t rec, int m, int n
 // global sums of PGURE::CalculatePGURE (pgure.hpp:136).  Fixed grid, fixed-order block reduction → the sums
 // are deterministic given the accumulators.  partial: gridDim.x * 5 doubles.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double norm_or_zero(double a, unsigned c)
-{
-    const double v = a / (double)c;
-    return isfinite(v) ? v : 0.0;
-}
 
 __global__ void k_risk(const double *__restrict__ u, const int8_t *__restrict__ d1, const int8_t *__restrict__ d2neg,
                        const unsigned *__restrict__ cnt, const double *__restrict__ acc0, const double *__restrict__ acc1,

@@ -64,7 +64,10 @@ struct pguresvt_handle
     size_t rec = 0;
     int nobj = 1;
     int objs[4] = {0, 0, 0, 0}; // SVT objects present: 0:U 1:U1 2:U2p 3:U2m
-    bool use_reg_svd = false;
+    bool use_reg_svd = false; // any register-resident 16x15 kernel
+    bool use_l4 = false;      // 4-lanes-per-matrix kernel (S in slot order, S[15] = sigma_max)
+    bool use_fused_eval = false;
+    int eval_blocks = 0;
     int sm_count = 148;
     double vP = 0, d2Neg = 0, d2Pos = 0;
     int64_t seed_used = 0;
@@ -79,7 +82,7 @@ struct pguresvt_handle
     double *dAcc[4] = {nullptr, nullptr, nullptr, nullptr};
     double *dFac[4] = {nullptr, nullptr, nullptr, nullptr};
     int8_t *dD1 = nullptr, *dD2 = nullptr;
-    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr;
+    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dInvCnt = nullptr, *dPartialE = nullptr;
     double *dY = nullptr, *dEst = nullptr, *dV = nullptr;
     int *dSweeps = nullptr;
     unsigned long long *dNcost = nullptr;
@@ -139,7 +142,7 @@ static void free_all(pguresvt_handle *h)
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dMot), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
-    F(h->dD1), F(h->dD2), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
+    F(h->dD1), F(h->dD2), F(h->dInvCnt), F(h->dPartialE), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
     h->noise_ws.release();
     if (h->hOut)
@@ -218,8 +221,10 @@ static int create_impl(pguresvt_handle *h)
         h->objs[h->nobj++] = 3;
     }
     h->use_reg_svd = (h->m == 16 && h->n == 15 && p.svd_kernel != 1);
-    if (p.svd_kernel == 2 && !h->use_reg_svd)
-        return fail(PGS_ERR_UNSUPPORTED, "register SVD kernel only covers 16x15 Casorati matrices");
+    if (p.svd_kernel >= 2 && !h->use_reg_svd)
+        return fail(PGS_ERR_UNSUPPORTED, "register SVD kernels only cover 16x15 Casorati matrices");
+    h->use_l4 = h->use_reg_svd && p.svd_kernel != 2;
+    h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
     {
         const double kappa = 1.;
         h->vP = 0.5 + 0.5 * kappa / std::sqrt(kappa * kappa + 4);
@@ -251,7 +256,8 @@ static int create_impl(pguresvt_handle *h)
     for (int k = 0; k < h->nobj; k++)
     {
         const int o = h->objs[k];
-        CU(cudaMalloc(&h->dAcc[o], wtot * sizeof(double)));
+        if (o == 0 || !h->use_fused_eval)
+            CU(cudaMalloc(&h->dAcc[o], wtot * sizeof(double)));
         CU(cudaMalloc(&h->dFac[o], h->rec * (size_t)h->P * sizeof(double)));
         CU(cudaMemset(h->dFac[o], 0, h->rec * (size_t)h->P * sizeof(double)));
     }
@@ -259,6 +265,12 @@ static int create_impl(pguresvt_handle *h)
     {
         CU(cudaMalloc(&h->dD1, wtot));
         CU(cudaMalloc(&h->dD2, wtot));
+    }
+    if (h->use_fused_eval)
+    {
+        h->eval_blocks = cdiv((long long)h->P * 16, 128);
+        CU(cudaMalloc(&h->dInvCnt, wtot * sizeof(double)));
+        CU(cudaMalloc(&h->dPartialE, (size_t)h->eval_blocks * sizeof(double)));
     }
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
@@ -595,7 +607,18 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
     pt.dPos = h->d2Pos;
     const int max_sweeps = 30;
     const double tol = 1e-15, tol2 = tol * tol;
-    if (h->use_reg_svd)
+    if (h->use_l4)
+    {
+        const long long nthreads = (long long)h->P * 4;
+        const double big = 1e-6, big2 = big * big;
+        if (obj == 0)
+            k_svd16_l4<0><<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
+                                                                  nullptr, max_sweeps, tol2, big2, h->dSweeps);
+        else // perturbed objects start from the V of object 0 (computed first for this frame)
+            k_svd16_l4<1><<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
+                                                                  h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
+    }
+    else if (h->use_reg_svd)
     {
         const long long nthreads = (long long)h->P * 8;
         k_svd_16x15<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
@@ -663,8 +686,39 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
 
 // One evaluation of PGURE::CalculatePGURE (pgure.hpp:120-137).  (alpha, mu, sigma) are the PGURE object's
 // members, i.e. AFTER the sigma/mu swap of pguresvt.hpp:133.
+static int objective_fused(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
+{
+    const size_t wtot = h->fsz * h->win;
+    CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
+    k_eval3<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N, lambda,
+                                               h->p.exp_weighting, h->dInvCnt, h->dD2, h->d2Neg, h->d2Pos, h->dAcc[0], h->dPartialE);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 1024, 0, h->st>>>(h->dPartialE, h->eval_blocks, 1, h->dOut + 2);
+    LAUNCHED(h);
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartial);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 2, h->dOut);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hOut, h->dOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
+    const double sigmasq = sigma * sigma;
+    const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
+    const double OoN = 1.0 / ((double)h->N * h->N * h->win);
+    *value = OoN * (s1 - (alpha + mu) * s2 + (2 / eps1 * s3) - (2 * sigmasq * alpha / (eps2 * eps2) * s4) + (2 * mu * s5) + mu) -
+             sigmasq;
+    if (terms)
+    {
+        terms[0] = s1, terms[1] = s2, terms[2] = s3, terms[3] = s4, terms[4] = s5;
+    }
+    h->stats[2] += 1;
+    return PGS_OK;
+}
+
 static int objective(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
 {
+    if (h->use_fused_eval)
+        return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
     for (int k = 0; k < h->nobj; k++)
     {
         int rc = launch_recon(h, h->objs[k], lambda, -1);
@@ -753,6 +807,12 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     {
         if ((rc = stage_count(h, -1)))
             return rc;
+        if (h->use_fused_eval)
+        {
+            const size_t wtot = h->fsz * h->win;
+            k_invcnt<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, wtot, h->dInvCnt);
+            LAUNCHED(h);
+        }
         if ((rc = sum_u(h, &h->cur_sumU)))
             return rc;
     }
@@ -1001,6 +1061,8 @@ extern "C" int pguresvt_probe_singular_values(pguresvt_handle *h, uint32_t t, in
         const size_t soff = (size_t)h->m * h->n + (size_t)h->ldv * h->n;
         CU(cudaMemcpy2D(S, (size_t)h->n * sizeof(double), h->dFac[obj] + soff, h->rec * sizeof(double), (size_t)h->n * sizeof(double),
                         h->P, cudaMemcpyDeviceToHost));
+        for (int q = 0; q < h->P; q++) // the 4-lane kernel keeps slot order; report LAPACK's descending order
+            std::sort(S + (size_t)q * h->n, S + (size_t)(q + 1) * h->n, [](double a, double b) { return a > b; });
     }
     return PGS_OK;
 }

@@ -104,7 +104,7 @@ def test_arps_motion_estimation_off_leaves_zero_positions(ref_test_cube):
 
 
 # ------------------------------------------------------------------ SVD / reconstruct / risk
-@pytest.mark.parametrize("svd_kernel", [0, 1])
+@pytest.mark.parametrize("svd_kernel", [0, 1, 2])
 def test_singular_values_vs_lapack(golden, svd_kernel):
     X = golden["X"]
     t, fw = 8, 7
@@ -117,6 +117,38 @@ def test_singular_values_vs_lapack(golden, svd_kernel):
     So = o.singular_values()
     assert S.shape == So.shape
     assert np.abs(S - So).max() / So.max() < 1e-12
+    h.close()
+
+
+@pytest.mark.parametrize("obj", [2, 3])
+def test_singular_values_of_perturbed_objects_warm_start(golden, obj):
+    """SVT objects U +- eps2*delta2 (pgure.hpp:81-82) are decomposed with a warm start from object 0's V; their
+    singular values must still be LAPACK's."""
+    X = golden["X"]
+    t, fw = 8, 7
+    h = bridge.Handle(X, optimize_pgure=True, noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03, random_seed=1)
+    S = h.probe_singular_values(t, obj)
+    u = X[:, :, t - fw:t + fw + 1].astype(np.float64)
+    u /= u.max()
+    _, d2 = orc.perturbations(1, u.size)
+    d2 = d2.reshape(u.shape, order="F")
+    up = u + (d2 * 0.01) if obj == 2 else u - (d2 * 0.01)
+    o = orc.SVTObj(golden["patches8"].astype(np.int64), 32, 15, 4, 1, True)
+    o.decompose(up)
+    So = o.singular_values()
+    assert np.abs(S - So).max() / So.max() < 1e-12
+    h.close()
+
+
+@pytest.mark.parametrize("svd_kernel", [1, 2])
+def test_pgure_objective_other_svd_kernels(golden, svd_kernel):
+    """The generic (shared-memory) and 8-lane register SVD kernels feed the unfused evaluation path."""
+    X = golden["X"]
+    alpha, mu, sigma = golden["pgure_params"]
+    h = bridge.Handle(X, optimize_pgure=True, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1,
+                      svd_kernel=svd_kernel)
+    vals, terms = h.probe_pgure(8, alpha, mu, sigma, golden["pgure_lambdas"])
+    assert np.abs(vals - golden["pgure_values"]).max() <= 1e-9 * np.abs(golden["pgure_values"]).max()
     h.close()
 
 
