@@ -864,6 +864,8 @@ __global__ void __launch_bounds__(128, 2)
     const int id = ids[pidx];
     const size_t fsz = (size_t)N * N;
 
+    // slot 0 is the fixed seat of the round-robin schedule: it holds the zero padding column, so slot pair 0 is a
+    // no-op in every round and is skipped statically; real column k lives in slot k+1
     double a[4][16];
 #pragma unroll
     for (int k = 0; k < SVD16_N; k++)
@@ -872,20 +874,21 @@ __global__ void __launch_bounds__(128, 2)
         const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * k;
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            a[r][k] = load_perturbed(u, vox + r, pt);
+            a[r][k + 1] = load_perturbed(u, vox + r, pt);
     }
 #pragma unroll
     for (int r = 0; r < 4; r++)
-        a[r][15] = 0.0;
+        a[r][0] = 0.0;
 
     if (WARM)
-    { // rows of A times V0 (column-major, ld 16) — each row independently, in place
+    { // rows of A times V0 (column-major, ld 16): each row independently; the 15 results of a row are parked in a
+      // lane-private shared-memory column so that the register file never holds two copies of the matrix
+        __shared__ double stage[SVD16_N][128];
         const double *V0 = fac0 + (size_t)SVD16_REC * pidx + SVD16_M * SVD16_N;
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
-            double t[SVD16_N];
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < SVD16_N; j++)
             {
                 const double2 *col = reinterpret_cast<const double2 *>(V0 + SVD16_LDV * j);
@@ -894,15 +897,15 @@ __global__ void __launch_bounds__(128, 2)
                 for (int i2 = 0; i2 < 8; i2++)
                 {
                     const double2 v = col[i2];
-                    acc = fma(a[r][2 * i2], v.x, acc);
+                    acc = fma(a[r][2 * i2 + 1], v.x, acc);
                     if (2 * i2 + 1 < SVD16_N)
-                        acc = fma(a[r][2 * i2 + 1], v.y, acc);
+                        acc = fma(a[r][2 * i2 + 2], v.y, acc);
                 }
-                t[j] = acc;
+                stage[j][threadIdx.x] = acc;
             }
 #pragma unroll
             for (int j = 0; j < SVD16_N; j++)
-                a[r][j] = t[j];
+                a[r][j + 1] = stage[j][threadIdx.x];
         }
     }
 
@@ -915,8 +918,9 @@ __global__ void __launch_bounds__(128, 2)
         for (int round = 0; round < 15; round++)
         {
             double pa[8], pb[8], pg[8];
+            pa[0] = pb[0] = pg[0] = 0.0;
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 1; i < 8; i++)
             {
                 double sa = 0.0, sb = 0.0, sg = 0.0;
 #pragma unroll
@@ -939,7 +943,7 @@ __global__ void __launch_bounds__(128, 2)
             jacobi_cs_fast(A0, B0, G0, tol2, big2, c0, s0, big);
             jacobi_cs_fast(A1, B1, G1, tol2, big2, c1, s1, big);
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 1; i < 8; i++)
             {
                 const double ci = __shfl_sync(0xffffffffu, (i & 1) ? c1 : c0, i >> 1, 4);
                 const double si = __shfl_sync(0xffffffffu, (i & 1) ? s1 : s0, i >> 1, 4);
@@ -986,11 +990,14 @@ __global__ void __launch_bounds__(128, 2)
     double n2[16], q[4];
 #pragma unroll
     for (int j = 0; j < 16; j++)
-    {
+    { // n2[j] = squared norm of column j (slot j+1); n2[15] = 0
         double sacc = 0.0;
+        if (j < SVD16_N)
+        {
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-            sacc = fma(a[r][j], a[r][j], sacc);
+            for (int r = 0; r < 4; r++)
+                sacc = fma(a[r][j + 1], a[r][j + 1], sacc);
+        }
         n2[j] = sacc;
     }
     tr4_16(n2, sub, q);
@@ -1003,9 +1010,20 @@ __global__ void __launch_bounds__(128, 2)
     for (int j = 0; j < SVD16_N; j++)
         smax = fmax(smax, sig[j]);
 
+    // descending order like LAPACK (svt.hpp:111): rank of every column, computed redundantly by every lane
+    int rk[SVD16_N];
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+    {
+        int rr = 0;
+#pragma unroll
+        for (int t2 = 0; t2 < SVD16_N; t2++)
+            rr += (sig[t2] > sig[j] || (sig[t2] == sig[j] && t2 < j)) ? 1 : 0;
+        rk[j] = rr;
+    }
     double *R = fac + (size_t)SVD16_REC * pidx;
     // U = W / sigma (columns with sigma below 1e-20 sigma_max carry nothing after thresholding: set to zero);
-    // afterwards a[r][j] holds z = w / sigma^2 for the V rebuild
+    // afterwards a[r][j+1] holds z = w / sigma^2 for the V rebuild
 #pragma unroll
     for (int j = 0; j < SVD16_N; j++)
     {
@@ -1014,23 +1032,27 @@ __global__ void __launch_bounds__(128, 2)
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
-            uu[r] = a[r][j] * inv;
-            a[r][j] = uu[r] * inv;
+            uu[r] = a[r][j + 1] * inv;
+            a[r][j + 1] = uu[r] * inv;
         }
         if (valid)
         {
-            double2 *dst = reinterpret_cast<double2 *>(R + SVD16_M * j + 4 * sub);
+            double2 *dst = reinterpret_cast<double2 *>(R + SVD16_M * rk[j] + 4 * sub);
             dst[0] = make_double2(uu[0], uu[1]);
             dst[1] = make_double2(uu[2], uu[3]);
+            if ((j >> 2) == sub)
+                R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + rk[j]] = sig[j];
         }
     }
-    if (valid)
+    if (valid && sub == 3)
+        R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 15] = smax; // slot 15 carries sigma_max
+    // ranks of the four columns this lane ends up with in the V rebuild (k = 4*sub + kl)
+    int rkm[4];
+#pragma unroll
+    for (int kl = 0; kl < 4; kl++)
     {
-        double *S = R + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
-        // lane `sub` writes S[4*sub .. 4*sub+3]; slot 15 carries sigma_max
-        double2 *dst = reinterpret_cast<double2 *>(S + 4 * sub);
-        dst[0] = make_double2(sig[4 * sub], sig[4 * sub + 1]);
-        dst[1] = make_double2(sig[4 * sub + 2], (sub == 3) ? smax : sig[4 * sub + 3]);
+        const int r0 = rk[kl], r1 = rk[4 + kl], r2 = rk[8 + kl], r3 = (12 + kl < SVD16_N) ? rk[(12 + kl < SVD16_N) ? 12 + kl : 0] : 0;
+        rkm[kl] = (sub == 0) ? r0 : (sub == 1) ? r1 : (sub == 2) ? r2 : r3;
     }
     // V(i, k) = sum_rows A(row, i) * z(row, k): loop over i, reduce over the 4 lanes, lane `sub` keeps k = 4*sub..4*sub+3;
     // four consecutive i are buffered so that each store is 4 contiguous doubles of one column of V
@@ -1060,7 +1082,7 @@ __global__ void __launch_bounds__(128, 2)
                     {
 #pragma unroll
                         for (int r = 0; r < 4; r++)
-                            sacc = fma(ao[r], a[r][k], sacc);
+                            sacc = fma(ao[r], a[r][k + 1], sacc);
                     }
                     part[k] = sacc;
                 }
@@ -1085,7 +1107,7 @@ __global__ void __launch_bounds__(128, 2)
                 const int k = 4 * sub + kl;
                 if (k < SVD16_N)
                 {
-                    double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * k + i0);
+                    double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * rkm[kl] + i0);
                     dst[0] = make_double2(vb[kl][0], vb[kl][1]);
                     dst[1] = make_double2(vb[kl][2], vb[kl][3]);
                 }
@@ -1093,7 +1115,10 @@ __global__ void __launch_bounds__(128, 2)
         }
     }
     if (sweeps_out && (threadIdx.x & 31) == 0)
+    {
         atomicMax(sweeps_out, sweep);
+        atomicAdd(sweeps_out + 1, sweep);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1111,128 +1136,190 @@ __device__ __forceinline__ double soft_f(double s, double smax, double lambda, i
     return fmax(s - w, 0.0); // s >= 0 from the Jacobi kernels
 }
 
-__global__ void __launch_bounds__(128)
+// cp.async helpers (16-byte global -> shared copies that bypass L1; completion tracked per thread in groups)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NN>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
+}
+
+#define EV_C 3                      /* singular triplets staged per chunk */
+#define EV_CH (3 * EV_C * 32)       /* doubles per chunk: 3 objects x C columns x (16 of U | 16 of V) */
+#define EV_GRP (48 + 2 * EV_CH)     /* doubles of shared memory per patch: S of 3 objects | two chunk buffers */
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
-            const double *__restrict__ invcnt, const int8_t *__restrict__ d2neg, double dNeg, double dPos,
-            double *__restrict__ acc0, double *__restrict__ partial)
+            double *__restrict__ acc0, double *__restrict__ accT)
 {
+    // 16 lanes per patch; lane g owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices.
+    // The factor records are streamed through shared memory with 16-byte cp.async copies: the singular values of
+    // the three objects and the first EV_C singular triplets are requested up front (before anything depends on
+    // them), further chunks of EV_C triplets are double-buffered behind the arithmetic.  Singular values are sorted
+    // descending and the soft threshold is monotone, so the surviving triplets are a prefix: nothing beyond the
+    // largest surviving index is ever fetched.  Two accumulators per entry: a0 = block of Uhat, t = b2p + b2m - 2 b0
+    // (the second difference the risk needs, linear in the blocks); both are overlap-added with fire-and-forget
+    // FP64 REDs — per slice the 16 lanes cover the patch's 4 x 4 footprint.
+    __shared__ __align__(16) double smem[8 * EV_GRP];
     const int lane = threadIdx.x & 31;
-    const int g = threadIdx.x & 15; // row of the block owned by this lane; also the slot whose threshold it computes
+    const int g = threadIdx.x & 15;
+    double *sg = smem + (threadIdx.x >> 4) * EV_GRP;
     int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool valid = pidx < P;
     if (!valid)
         pidx = P - 1;
     const size_t roff = (size_t)SVD16_REC * pidx;
-    const double *R0 = fac0 + roff, *R2 = fac2 + roff, *R3 = fac3 + roff;
+    const double *R[3] = {fac0 + roff, fac2 + roff, fac3 + roff};
     const int soff = SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
-    double f0, f2, f3;
+    // ---- requests: S (lanes 0..7 copy 16 bytes of each object's S), chunk 0
+    if (g < 8)
     {
-        const double sm0 = R0[soff + 15], sm2 = R2[soff + 15], sm3 = R3[soff + 15];
-        f0 = (g < SVD16_N) ? soft_f(R0[soff + g], sm0, lambda, expw) : 0.0;
-        f2 = (g < SVD16_N) ? soft_f(R2[soff + g], sm2, lambda, expw) : 0.0;
-        f3 = (g < SVD16_N) ? soft_f(R3[soff + g], sm3, lambda, expw) : 0.0;
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+            cp_async16(sg + 16 * o + 2 * g, R[o] + soff + 2 * g);
     }
-    unsigned m = __ballot_sync(0xffffffffu, (f0 != 0.0) || (f2 != 0.0) || (f3 != 0.0));
-    m = (m | (m >> 16)) & 0xffffu; // union over the two patches of the warp: uniform trip count
-    double a0[SVD16_N], a2[SVD16_N], a3[SVD16_N];
+    auto request_chunk = [&](int c0, int buf) {
+        double *dst = sg + 48 + buf * EV_CH;
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+#pragma unroll
+            for (int c = 0; c < EV_C; c++)
+            {
+                const int kk = c0 + c;
+                if (kk < SVD16_N)
+                {
+                    // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
+                    const double *src = (g < 8) ? R[o] + SVD16_M * kk + 2 * g : R[o] + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
+                    cp_async16(dst + (o * EV_C + c) * 32 + 2 * g, src);
+                }
+            }
+    };
+    request_chunk(0, 0);
+    cp_async_commit();
+    // trajectory (independent of the factor data)
+    const int id = ids[pidx];
+    const int r = g & 3, c = g >> 2;
+    const int fsz = N * N;
+    int vox[SVD16_N];
 #pragma unroll
     for (int k = 0; k < SVD16_N; k++)
-        a0[k] = a2[k] = a3[k] = 0.0;
-    while (m)
     {
-        const int kk = __ffs(m) - 1;
-        m &= m - 1;
-        const int src = (lane & 16) | kk;
-        const double fk0 = __shfl_sync(0xffffffffu, f0, src);
-        const double fk2 = __shfl_sync(0xffffffffu, f2, src);
-        const double fk3 = __shfl_sync(0xffffffffu, f3, src);
-        const double u0 = R0[SVD16_M * kk + g] * fk0;
-        const double u2 = R2[SVD16_M * kk + g] * fk2;
-        const double u3 = R3[SVD16_M * kk + g] * fk3;
-        const double2 *v0 = reinterpret_cast<const double2 *>(R0 + SVD16_M * SVD16_N + SVD16_LDV * kk);
-        const double2 *v2 = reinterpret_cast<const double2 *>(R2 + SVD16_M * SVD16_N + SVD16_LDV * kk);
-        const double2 *v3 = reinterpret_cast<const double2 *>(R3 + SVD16_M * SVD16_N + SVD16_LDV * kk);
+        const short2 p = pos[(size_t)k * vecSize + id];
+        vox[k] = (p.x + r) + N * (p.y + c) + fsz * k;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    // ---- thresholds: lane g handles slot g of each object
+    double f0, f2, f3;
+    {
+        const double sm0 = sg[15], sm2 = sg[16 + 15], sm3 = sg[32 + 15];
+        f0 = (g < SVD16_N) ? soft_f(sg[g], sm0, lambda, expw) : 0.0;
+        f2 = (g < SVD16_N) ? soft_f(sg[16 + g], sm2, lambda, expw) : 0.0;
+        f3 = (g < SVD16_N) ? soft_f(sg[32 + g], sm3, lambda, expw) : 0.0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, (f0 != 0.0) || (f2 != 0.0) || (f3 != 0.0));
+    m = (m | (m >> 16)) & 0xffffu;
+    const int Kw = 32 - __clz(m); // one past the largest surviving index over both patches of the warp (0 if none)
+    double a0[SVD16_N], t[SVD16_N];
 #pragma unroll
-        for (int k2 = 0; k2 < 8; k2++)
+    for (int k = 0; k < SVD16_N; k++)
+        a0[k] = t[k] = 0.0;
+    int buf = 0;
+    for (int c0 = 0; c0 < Kw; c0 += EV_C)
+    {
+        if (c0 + EV_C < Kw)
+            request_chunk(c0 + EV_C, buf ^ 1);
+        cp_async_commit();
+        const double *cb = sg + 48 + buf * EV_CH;
+#pragma unroll
+        for (int cc = 0; cc < EV_C; cc++)
         {
-            const double2 x0 = v0[k2], x2 = v2[k2], x3 = v3[k2];
-            a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
-            a2[2 * k2] = fma(u2, x2.x, a2[2 * k2]);
-            a3[2 * k2] = fma(u3, x3.x, a3[2 * k2]);
-            if (2 * k2 + 1 < SVD16_N)
+            const int kk = c0 + cc;
+            if (kk < Kw)
             {
-                a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
-                a2[2 * k2 + 1] = fma(u2, x2.y, a2[2 * k2 + 1]);
-                a3[2 * k2 + 1] = fma(u3, x3.y, a3[2 * k2 + 1]);
+                const int src = (lane & 16) | kk;
+                const double fk0 = __shfl_sync(0xffffffffu, f0, src);
+                const double fk2 = __shfl_sync(0xffffffffu, f2, src);
+                const double fk3 = __shfl_sync(0xffffffffu, f3, src);
+                const double *b0 = cb + (0 * EV_C + cc) * 32, *b2 = cb + (1 * EV_C + cc) * 32, *b3 = cb + (2 * EV_C + cc) * 32;
+                const double u0 = b0[g] * fk0, u2 = b2[g] * fk2, u3 = b3[g] * fk3;
+                const double um = -2.0 * u0;
+                const double2 *v0 = reinterpret_cast<const double2 *>(b0 + 16);
+                const double2 *v2 = reinterpret_cast<const double2 *>(b2 + 16);
+                const double2 *v3 = reinterpret_cast<const double2 *>(b3 + 16);
+#pragma unroll
+                for (int k2 = 0; k2 < 8; k2++)
+                {
+                    const double2 x0 = v0[k2], x2 = v2[k2], x3 = v3[k2];
+                    a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
+                    t[2 * k2] = fma(um, x0.x, fma(u2, x2.x, fma(u3, x3.x, t[2 * k2])));
+                    if (2 * k2 + 1 < SVD16_N)
+                    {
+                        a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
+                        t[2 * k2 + 1] = fma(um, x0.y, fma(u2, x2.y, fma(u3, x3.y, t[2 * k2 + 1])));
+                    }
+                }
             }
         }
+        cp_async_wait<0>();
+        __syncwarp();
+        buf ^= 1;
     }
-    double s4 = 0.0;
     if (valid)
     {
-        const int id = ids[pidx];
-        const size_t fsz = (size_t)N * N;
-        const int r = g & 3, c = g >> 2;
 #pragma unroll
         for (int k = 0; k < SVD16_N; k++)
         {
-            const short2 p = pos[(size_t)k * vecSize + id];
-            const size_t vox = (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k;
-            const double ic = invcnt[vox];
-            const double d2 = d2neg[vox] ? dNeg : dPos;
-            s4 = fma(d2 * ic, (a2[k] - 2 * a0[k]) + a3[k], s4);
-            atomicAdd(acc0 + vox, a0[k]);
+            atomicAdd(acc0 + vox[k], a0[k]);
+            atomicAdd(accT + vox[k], t[k]);
         }
     }
-    s4 = warp_sum(s4);
-    __shared__ double sm[4];
-    if (lane == 0)
-        sm[threadIdx.x >> 5] = s4;
-    __syncthreads();
-    if (threadIdx.x == 0)
-        partial[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
 }
 
-// 1 / weights (0 where no patch covers the voxel): svt.hpp:163-164 folded into a multiplier, once per frame
-__global__ void k_invcnt(const unsigned *__restrict__ cnt, size_t n, double *__restrict__ invcnt)
-{
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        invcnt[i] = cnt[i] ? 1.0 / (double)cnt[i] : 0.0;
-}
-
-// voxel pass of the fused evaluation: s1 = sum (Uhat - U)^2, s5 = sum Uhat with Uhat = acc0 / weights
-// partial: gridDim.x * 2 doubles
+// voxel pass of the fused evaluation: Uhat = acc0 / weights (non-finite -> 0, svt.hpp:163-164);
+// s1 = sum (Uhat - U)^2, s5 = sum Uhat, s4 = sum delta2 * (accT / weights)   [accT = U2p + U2m - 2 Uhat, unnormalised]
+// partial: gridDim.x * 3 doubles
 __global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, const double *__restrict__ acc0,
-                            size_t tot, double *__restrict__ partial)
+                            const double *__restrict__ accT, const int8_t *__restrict__ d2neg, double dNeg, double dPos, size_t tot,
+                            double *__restrict__ partial)
 {
-    double s1 = 0, s5 = 0;
+    double s1 = 0, s5 = 0, s4 = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
-        const double v0 = norm_or_zero(acc0[i], cnt[i]);
+        const unsigned c = cnt[i];
+        const double v0 = norm_or_zero(acc0[i], c);
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
         s5 += v0;
+        s4 = fma(d2neg[i] ? dNeg : dPos, norm_or_zero(accT[i], c), s4);
     }
-    __shared__ double sm[2][32];
+    __shared__ double sm[3][32];
     s1 = warp_sum(s1);
     s5 = warp_sum(s5);
+    s4 = warp_sum(s4);
     if ((threadIdx.x & 31) == 0)
     {
         sm[0][threadIdx.x >> 5] = s1;
         sm[1][threadIdx.x >> 5] = s5;
+        sm[2][threadIdx.x >> 5] = s4;
     }
     __syncthreads();
     if (threadIdx.x < 32)
     {
-        double r1 = (threadIdx.x < (blockDim.x >> 5)) ? sm[0][threadIdx.x] : 0.0;
-        double r5 = (threadIdx.x < (blockDim.x >> 5)) ? sm[1][threadIdx.x] : 0.0;
-        r1 = warp_sum(r1);
-        r5 = warp_sum(r5);
-        if (threadIdx.x == 0)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
         {
-            partial[(size_t)blockIdx.x * 2] = r1;
-            partial[(size_t)blockIdx.x * 2 + 1] = r5;
+            double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
+            r = warp_sum(r);
+            if (threadIdx.x == 0)
+                partial[(size_t)blockIdx.x * 3 + q] = r;
         }
     }
 }

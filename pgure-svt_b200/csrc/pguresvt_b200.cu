@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -82,7 +83,7 @@ struct pguresvt_handle
     double *dAcc[4] = {nullptr, nullptr, nullptr, nullptr};
     double *dFac[4] = {nullptr, nullptr, nullptr, nullptr};
     int8_t *dD1 = nullptr, *dD2 = nullptr;
-    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dInvCnt = nullptr, *dPartialE = nullptr;
+    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dAccT = nullptr;
     double *dY = nullptr, *dEst = nullptr, *dV = nullptr;
     int *dSweeps = nullptr;
     unsigned long long *dNcost = nullptr;
@@ -142,7 +143,7 @@ static void free_all(pguresvt_handle *h)
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dMot), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
-    F(h->dD1), F(h->dD2), F(h->dInvCnt), F(h->dPartialE), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
+    F(h->dD1), F(h->dD2), F(h->dAccT), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
     h->noise_ws.release();
     if (h->hOut)
@@ -269,15 +270,16 @@ static int create_impl(pguresvt_handle *h)
     if (h->use_fused_eval)
     {
         h->eval_blocks = cdiv((long long)h->P * 16, 128);
-        CU(cudaMalloc(&h->dInvCnt, wtot * sizeof(double)));
-        CU(cudaMalloc(&h->dPartialE, (size_t)h->eval_blocks * sizeof(double)));
+        if (wtot >= ((size_t)1 << 31))
+            return fail(PGS_ERR_UNSUPPORTED, "window of %zu voxels exceeds the fused evaluation kernel's 32-bit indexing", wtot);
+        CU(cudaMalloc(&h->dAccT, wtot * sizeof(double)));
     }
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
     CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
     CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
-    CU(cudaMalloc(&h->dSweeps, sizeof(int)));
+    CU(cudaMalloc(&h->dSweeps, 2 * sizeof(int)));
     CU(cudaMalloc(&h->dNcost, sizeof(unsigned long long)));
     CU(cudaMallocHost(&h->hOut, 16 * sizeof(double)));
     h->xmax.assign(nres, 0.0);
@@ -690,14 +692,21 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
 {
     const size_t wtot = h->fsz * h->win;
     CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
-    k_eval3<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N, lambda,
-                                               h->p.exp_weighting, h->dInvCnt, h->dD2, h->d2Neg, h->d2Pos, h->dAcc[0], h->dPartialE);
+    CU(cudaMemsetAsync(h->dAccT, 0, wtot * sizeof(double), h->st));
+    static const int minb = getenv("PGURESVT_EVAL_MINB") ? atoi(getenv("PGURESVT_EVAL_MINB")) : 4;
+    if (minb == 3)
+        k_eval3<3><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
+                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
+    else if (minb == 5)
+        k_eval3<5><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
+                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
+    else
+        k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
+                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
     LAUNCHED(h);
-    k_reduce_partials<<<1, 1024, 0, h->st>>>(h->dPartialE, h->eval_blocks, 1, h->dOut + 2);
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], h->dAccT, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dPartial);
     LAUNCHED(h);
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartial);
-    LAUNCHED(h);
-    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 2, h->dOut);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
     LAUNCHED(h);
     CU(cudaMemcpyAsync(h->hOut, h->dOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
@@ -794,25 +803,25 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     }
     {
         StageTimer tm(h, 5);
-        CU(cudaMemsetAsync(h->dSweeps, 0, sizeof(int), h->st));
         for (int k = 0; k < h->nobj; k++)
+        {
+            CU(cudaMemsetAsync(h->dSweeps, 0, 2 * sizeof(int), h->st));
             if ((rc = stage_svd(h, h->objs[k])))
                 return rc;
-        int sw = 0;
-        CU(cudaMemcpyAsync(&sw, h->dSweeps, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        CU(cudaStreamSynchronize(h->st));
-        h->stats[10] = std::max(h->stats[10], (double)sw);
+            int sw[2] = {0, 0};
+            CU(cudaMemcpyAsync(sw, h->dSweeps, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            h->stats[10] = std::max(h->stats[10], (double)sw[0]);
+            // mean sweeps per warp of object 0 ([12]) and of the warm-started objects ([13]) of the last frame
+            const double nwarps = std::ceil((double)h->P * (h->use_l4 ? 4 : 8) / 32.0);
+            if (h->use_reg_svd && h->use_l4)
+                h->stats[h->objs[k] == 0 ? 12 : 13] = sw[1] / nwarps;
+        }
     }
     if (h->p.optimize_pgure)
     {
         if ((rc = stage_count(h, -1)))
             return rc;
-        if (h->use_fused_eval)
-        {
-            const size_t wtot = h->fsz * h->win;
-            k_invcnt<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, wtot, h->dInvCnt);
-            LAUNCHED(h);
-        }
         if ((rc = sum_u(h, &h->cur_sumU)))
             return rc;
     }
