@@ -1,19 +1,923 @@
-// Noise estimation stage (src/noise.hpp:35-458) — GPU implementation.
+// Noise estimation stage — NoiseEstimator::Estimate (src/noise.hpp:35-153) on the GPU.
+//
+//   1. k_noise_split   F-test split decision of SplitBlockQ (noise.hpp:182-221) for EVERY dyadic block of every
+//                      level (s = N … 16) of every window slice in one launch per level — the decision depends only
+//                      on the block, so the quirky recursion (noise.hpp:419-458) is replayed afterwards
+//                      on the host against this table, which reproduces the reference's node multiset exactly
+//                      (root kept, tree built twice, duplicates counted twice).
+//   2. k_noise_leaf    one CTA per DISTINCT kept region: robust mean (IRLS with Huber weights and the interquartile
+//                      scale, noise.hpp:238-271 — the two order statistics of A are found once by radix select, since
+//                      sorting r = A - m is sorting A), Laplacian pseudo-residual (noise.hpp:395-417) and the MAD
+//                      variance (noise.hpp:232-236, medians by radix select).
+//   3. k_noise_wls     iteratively re-weighted least-squares line fit var = a*mean + b (noise.hpp:328-383) in one
+//                      CTA; the per-iteration IQR of the residuals is again a radix select.
+// The host only walks the quadtree (scalar, pointer-chasing) and applies the method-4 formulas (noise.hpp:139-146).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 namespace pgs
 {
-struct NoiseWorkspace
+
+struct NoiseRegion
 {
-    void release() {}
+    int i, j, s, slice; // rows i.., cols j.., side s (noise.hpp:75-77)
+    long long off;      // offset of this region's Laplacian scratch
 };
 
-static int noise_estimate_window(NoiseWorkspace &, const double *, int, int, int, int, cudaStream_t, double &, double &,
-                                 double &, long long *, std::string &err)
+// ---- block-wide helpers (blockDim.x threads, deterministic order) --------------------------------------
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sm)
 {
-    err = "noise estimation (noise_alpha/mu/sigma < 0) is not available on the GPU path yet";
-    return 3; // PGS_ERR_UNSUPPORTED
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++)
+        r += sm[w];
+    return r;
 }
+
+__device__ __forceinline__ unsigned long long key_of(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double val_of(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (0-based) of n values produced by get(e), e in [0,n): MSB-first radix select, 8 bits per pass.
+// All threads of the CTA must call it; hist = 256 ints + 2 words of shared memory.
+template <int NT, typename Get>
+__device__ double block_select(Get get, int n, int k, unsigned *hist, unsigned long long *spre)
+{
+    unsigned long long prefix = 0;
+    int kk = k;
+    for (int pass = 0; pass < 8; pass++)
+    {
+        const int shift = 56 - 8 * pass;
+        for (int b = threadIdx.x; b < 256; b += NT)
+            hist[b] = 0u;
+        __syncthreads();
+        // warp-aggregated histogram: values of one block share their top bytes, so un-aggregated shared-memory
+        // atomics would serialise on one or two bins
+        for (int e0 = 0; e0 < n; e0 += NT)
+        {
+            const int e = e0 + threadIdx.x;
+            unsigned bin = 256u; // "does not take part"
+            if (e < n)
+            {
+                const unsigned long long key = key_of(get(e));
+                const bool match = (pass == 0) || (((key ^ prefix) >> (shift + 8)) == 0ull);
+                if (match)
+                    bin = (unsigned)(key >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin < 256u && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32)
+        { // warp 0: each lane owns 8 consecutive bins
+            unsigned loc[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                loc[q] = hist[threadIdx.x * 8 + q];
+                tot += loc[q];
+            }
+            unsigned inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o)
+                    inc += t;
+            }
+            unsigned before = inc - tot; // elements in bins of lower lanes
+            if ((unsigned)kk >= before && (unsigned)kk < inc)
+            {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                {
+                    if ((unsigned)kk >= before && (unsigned)kk < before + loc[q])
+                    {
+                        spre[0] = prefix | ((unsigned long long)(threadIdx.x * 8 + q) << shift);
+                        spre[1] = (unsigned long long)((unsigned)kk - before);
+                    }
+                    before += loc[q];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = spre[0];
+        kk = (int)spre[1];
+        __syncthreads();
+    }
+    return val_of(prefix);
+}
+
+// ---- 1. split decisions ------------------------------------------------------------------------------
+// grid = (blocks per slice at this level, T); one CTA per block of side s.  flag = 1 if SplitBlockQ is true.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_noise_split(const double *__restrict__ u, int N, int s, double ftest, unsigned char *__restrict__ flags,
+                              int flags_per_slice, int level_off)
+{
+    __shared__ double sm[NT / 32];
+    const int nb = N / s;
+    const int bi = blockIdx.x % nb, bj = blockIdx.x / nb;
+    const double *A = u + (size_t)N * N * blockIdx.y + (size_t)(bi * s) + (size_t)N * (bj * s);
+    const int R = s * s;
+    const double isq = sqrt(30.0);
+    double sa = 0.0, sr = 0.0;
+    for (int e = threadIdx.x; e < R; e += NT)
+    {
+        const int y = e % s, x = e / s;
+        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+        const double a = A[y + (size_t)N * x];
+        const double res = (5.0 * a - (((A[yp + (size_t)N * x] + A[ym + (size_t)N * x]) + A[y + (size_t)N * xm]) + A[y + (size_t)N * xp])) / isq;
+        sa += a;
+        sr += res;
+    }
+    const double accuZ = block_sum<NT>(sa, sm) * (1.0 / R);
+    const double accuR = block_sum<NT>(sr, sm) * (1.0 / R);
+    double vz = 0.0, ve = 0.0;
+    for (int e = threadIdx.x; e < R; e += NT)
+    {
+        const int y = e % s, x = e / s;
+        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+        const double a = A[y + (size_t)N * x];
+        const double res = (5.0 * a - (((A[yp + (size_t)N * x] + A[ym + (size_t)N * x]) + A[y + (size_t)N * xm]) + A[y + (size_t)N * xp])) / isq;
+        const double dz = a - accuZ, de = res - accuR;
+        vz = fma(dz, dz, vz);
+        ve = fma(de, de, ve);
+    }
+    const double Sz = block_sum<NT>(vz, sm) * (1.0 / (R - 1));
+    const double Se = block_sum<NT>(ve, sm) * (1.0 / (R - 1));
+    if (threadIdx.x == 0)
+    {
+        const double stat = (Sz > Se) ? Sz / Se : Se / Sz;
+        flags[(size_t)flags_per_slice * blockIdx.y + level_off + blockIdx.x] = (stat > ftest) ? 1 : 0;
+    }
+}
+
+// ---- 2. leaf statistics ------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_noise_leaf(const double *__restrict__ u, int N, const NoiseRegion *__restrict__ regions,
+                             double *__restrict__ scratch, double *__restrict__ out /* 2 per region: mean, var */, int big_side)
+{
+    __shared__ double sm[NT / 32];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long spre[2];
+    const NoiseRegion rg = regions[blockIdx.x];
+    if (rg.s >= big_side)
+        return; // handled grid-wide by k_noise_big
+    const int s = rg.s, n = s * s;
+    const double *A = u + (size_t)N * N * rg.slice + (size_t)rg.i + (size_t)N * rg.j;
+    auto getA = [&](int e) { return A[(e % s) + (size_t)N * (e / s)]; };
+
+    // interquartile order statistics of A (InterquartileDistance, noise.hpp:223-230)
+    const int mq = (int)floor((floor((double)((n + 1) / 2)) + 1) / 2);
+    const double Alo = block_select<NT>(getA, n, mq - 1, hist, spre);
+    const double Ahi = block_select<NT>(getA, n, n - mq - 1, hist, spre);
+
+    // robust mean (RobustMeanEstimate, noise.hpp:238-271)
+    double m = 0.0, m0 = 1E12, mprev = 0.0, inv = 0.0;
+    const double tol = 1E-6, eps = 1E-12;
+    bool first = true;
+    for (int it = 0; it < 10000; it++)
+    {
+        double s1 = 0.0, s0 = 0.0;
+        for (int e = threadIdx.x; e < n; e += NT)
+        {
+            const double a = getA(e);
+            double w = 1.0;
+            if (!first)
+            {
+                const double r = fabs((a - mprev) * inv);
+                w = (r < 0.75) ? 1.0 : 0.75 / r;
+            }
+            s1 += w * a;
+            s0 += w;
+        }
+        const double S1 = block_sum<NT>(s1, sm), S0 = block_sum<NT>(s0, sm);
+        m = (fabs(S0) < eps) ? m0 : S1 / S0;
+        double se = 0.0;
+        for (int e = threadIdx.x; e < n; e += NT)
+            se += fabs(getA(e) - m);
+        const double ee = block_sum<NT>(se, sm) / (double)n;
+        if (fabs(m0 - m) < tol || ee < tol)
+            break;
+        m0 = m;
+        const double d = ((Ahi - m) - (Alo - m)) + eps;
+        inv = 1. / d;
+        mprev = m;
+        first = false;
+    }
+
+    // Laplacian pseudo-residual (ConvolveFIR, noise.hpp:395-417) into scratch
+    double *L = scratch + rg.off;
+    for (int e = threadIdx.x; e < n; e += NT)
+    {
+        const int y = e % s, x = e / s; // (x, y) as in the reference's loops
+        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+#define IN_(a, b) A[(a) + (size_t)N * (b)]
+        // neighbours (rows filled first), multiplied by -laplacian, accumulated in column-major two-accumulator order
+        const double t0 = IN_(xm, ym) * -0.125, t1 = IN_(xm, y) * -0.125, t2 = IN_(xm, yp) * -0.125;
+        const double t3 = IN_(x, ym) * -0.125, t4 = IN_(x, y) * 1.0, t5 = IN_(x, yp) * -0.125;
+        const double t6 = IN_(xp, ym) * -0.125, t7 = IN_(xp, y) * -0.125, t8 = IN_(xp, yp) * -0.125;
+#undef IN_
+        const double v1 = (((t0 + t2) + t4) + t6) + t8;
+        const double v2 = ((t1 + t3) + t5) + t7;
+        L[e] = v1 + v2;
+    }
+    __syncthreads();
+    auto getL = [&](int e) { return L[e]; };
+    // arma::median of an even-length vector: nth = n/2, plus the largest of the lower half
+    const double l1 = block_select<NT>(getL, n, n / 2, hist, spre);
+    const double l2 = block_select<NT>(getL, n, n / 2 - 1, hist, spre);
+    const double med = l1 + (l2 - l1) / 2.0;
+    auto getD = [&](int e) { return fabs(L[e] - med); };
+    const double d1 = block_select<NT>(getD, n, n / 2, hist, spre);
+    const double d2 = block_select<NT>(getD, n, n / 2 - 1, hist, spre);
+    const double mad = d1 + (d2 - d1) / 2.0;
+    if (threadIdx.x == 0)
+    {
+        const double sig = 1.4826 * mad;
+        out[2 * (size_t)blockIdx.x] = m;
+        out[2 * (size_t)blockIdx.x + 1] = sig * sig;
+    }
+}
+
+// ---- grid-wide (cooperative launch) versions for the large regions and the line fit -------------------
+// Large regions (the whole-frame root node of every slice is always kept) and the ~5e5-sample line fit
+// are latency-bound inside one CTA; here the same algorithms run on one CTA per SM with grid-wide reductions:
+// per-CTA partials in a rotating slot + grid.sync, and radix-select histograms merged through a small ring of
+// global 256-bin histograms (a slot is re-zeroed one pass after it was read).
+namespace cg = cooperative_groups;
+
+struct GridScratch
+{
+    double *partials; // [4][8][grid]
+    unsigned *ghist;  // [4][256], zero at launch
+    int *counters;    // unused by the device; host zeroes ghist before every launch
+};
+
+template <int NT, int NQ>
+__device__ __forceinline__ void grid_sum(const double (&v)[NQ], double (&out)[NQ], cg::grid_group &grid, const GridScratch &gs,
+                                         unsigned &slot, double *sm)
+{
+    double *P = gs.partials + (size_t)(slot & 3u) * 8 * gridDim.x;
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+    {
+        const double b = block_sum<NT>(v[q], sm);
+        if (threadIdx.x == 0)
+            P[(size_t)q * gridDim.x + blockIdx.x] = b;
+    }
+    grid.sync();
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+    {
+        double r = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++)
+            r += P[(size_t)q * gridDim.x + b];
+        out[q] = r;
+    }
+    slot++;
+}
+
+template <int NT, typename Get>
+__device__ double grid_select(Get get, int n, int k, cg::grid_group &grid, const GridScratch &gs, unsigned &hslot, unsigned *hist,
+                              unsigned long long *spre)
+{
+    unsigned long long prefix = 0;
+    int kk = k;
+    const int stride = gridDim.x * NT;
+    for (int pass = 0; pass < 8; pass++)
+    {
+        const int shift = 56 - 8 * pass;
+        unsigned *G = gs.ghist + (size_t)(hslot & 3u) * 256;
+        for (int b = threadIdx.x; b < 256; b += NT)
+            hist[b] = 0u;
+        __syncthreads();
+        for (int e0 = blockIdx.x * NT; e0 < n; e0 += stride)
+        {
+            const int e = e0 + threadIdx.x;
+            unsigned bin = 256u;
+            if (e < n)
+            {
+                const unsigned long long key = key_of(get(e));
+                const bool match = (pass == 0) || (((key ^ prefix) >> (shift + 8)) == 0ull);
+                if (match)
+                    bin = (unsigned)(key >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin < 256u && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < 256; b += NT)
+            if (hist[b])
+                atomicAdd(&G[b], hist[b]);
+        grid.sync();
+        // the slot read one pass ago is no longer in use by anybody: clear it for its next turn
+        if (blockIdx.x == 0)
+            for (int b = threadIdx.x; b < 256; b += NT)
+                gs.ghist[(size_t)((hslot + 3u) & 3u) * 256 + b] = 0u;
+        if (threadIdx.x < 32)
+        {
+            unsigned loc[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                loc[q] = G[threadIdx.x * 8 + q];
+                tot += loc[q];
+            }
+            unsigned inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o)
+                    inc += t;
+            }
+            unsigned before = inc - tot;
+            if ((unsigned)kk >= before && (unsigned)kk < inc)
+            {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                {
+                    if ((unsigned)kk >= before && (unsigned)kk < before + loc[q])
+                    {
+                        spre[0] = prefix | ((unsigned long long)(threadIdx.x * 8 + q) << shift);
+                        spre[1] = (unsigned long long)((unsigned)kk - before);
+                    }
+                    before += loc[q];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = spre[0];
+        kk = (int)spre[1];
+        __syncthreads();
+        hslot++;
+    }
+    return val_of(prefix);
+}
+
+// all large regions, one after the other, each spread over the whole grid.  Same maths as k_noise_leaf.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_noise_big(const double *__restrict__ u, int N, const NoiseRegion *__restrict__ regions,
+                                                  const int *__restrict__ big_idx, int nbig, double *__restrict__ scratch,
+                                                  double *__restrict__ out, GridScratch gs)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[NT / 32];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long spre[2];
+    unsigned slot = 0, hslot = 0;
+    const int gstride = gridDim.x * NT;
+    for (int bq = 0; bq < nbig; bq++)
+    {
+        const int ridx = big_idx[bq];
+        const NoiseRegion rg = regions[ridx];
+        const int s = rg.s, n = s * s, sh = 31 - __clz(s); // s is a power of two
+        const double *A = u + (size_t)N * N * rg.slice + (size_t)rg.i + (size_t)N * rg.j;
+        auto getA = [&](int e) { return A[(e & (s - 1)) + (size_t)N * (e >> sh)]; };
+        const int mq = (int)floor((floor((double)((n + 1) / 2)) + 1) / 2);
+        const double Alo = grid_select<NT>(getA, n, mq - 1, grid, gs, hslot, hist, spre);
+        const double Ahi = grid_select<NT>(getA, n, n - mq - 1, grid, gs, hslot, hist, spre);
+        double m = 0.0, m0 = 1E12, mprev = 0.0, inv = 0.0;
+        const double tol = 1E-6, eps = 1E-12;
+        bool first = true;
+        for (int it = 0; it < 10000; it++)
+        {
+            double v2[2] = {0.0, 0.0}, o2[2];
+            for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+            {
+                const double a = getA(e);
+                double w = 1.0;
+                if (!first)
+                {
+                    const double r = fabs((a - mprev) * inv);
+                    w = (r < 0.75) ? 1.0 : 0.75 / r;
+                }
+                v2[0] += w * a;
+                v2[1] += w;
+            }
+            grid_sum<NT, 2>(v2, o2, grid, gs, slot, sm);
+            m = (fabs(o2[1]) < eps) ? m0 : o2[0] / o2[1];
+            double v1[1] = {0.0}, o1[1];
+            for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+                v1[0] += fabs(getA(e) - m);
+            grid_sum<NT, 1>(v1, o1, grid, gs, slot, sm);
+            const double ee = o1[0] / (double)n;
+            if (fabs(m0 - m) < tol || ee < tol)
+                break;
+            m0 = m;
+            const double d = ((Ahi - m) - (Alo - m)) + eps;
+            inv = 1. / d;
+            mprev = m;
+            first = false;
+        }
+        double *L = scratch + rg.off;
+        for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+        {
+            const int y = e & (s - 1), x = e >> sh;
+            const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+            const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+#define IN_(a, b) A[(a) + (size_t)N * (b)]
+            const double t0 = IN_(xm, ym) * -0.125, t1 = IN_(xm, y) * -0.125, t2 = IN_(xm, yp) * -0.125;
+            const double t3 = IN_(x, ym) * -0.125, t4 = IN_(x, y) * 1.0, t5 = IN_(x, yp) * -0.125;
+            const double t6 = IN_(xp, ym) * -0.125, t7 = IN_(xp, y) * -0.125, t8 = IN_(xp, yp) * -0.125;
+#undef IN_
+            const double v1 = (((t0 + t2) + t4) + t6) + t8;
+            const double v2 = ((t1 + t3) + t5) + t7;
+            L[e] = v1 + v2;
+        }
+        grid.sync();
+        auto getL = [&](int e) { return L[e]; };
+        const double l1 = grid_select<NT>(getL, n, n / 2, grid, gs, hslot, hist, spre);
+        const double l2 = grid_select<NT>(getL, n, n / 2 - 1, grid, gs, hslot, hist, spre);
+        const double med = l1 + (l2 - l1) / 2.0;
+        auto getD = [&](int e) { return fabs(L[e] - med); };
+        const double d1 = grid_select<NT>(getD, n, n / 2, grid, gs, hslot, hist, spre);
+        const double d2 = grid_select<NT>(getD, n, n / 2 - 1, grid, gs, hslot, hist, spre);
+        const double mad = d1 + (d2 - d1) / 2.0;
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            const double sig = 1.4826 * mad;
+            out[2 * (size_t)ridx] = m;
+            out[2 * (size_t)ridx + 1] = sig * sig;
+        }
+    }
+}
+
+// grid-wide WLSFit (noise.hpp:328-383) over the (mean, variance) samples of all window slices
+template <int NT>
+__global__ void __launch_bounds__(NT) k_noise_wls_grid(const double *__restrict__ xs, const double *__restrict__ ys, int n,
+                                                       double *__restrict__ out, GridScratch gs)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[NT / 32];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long spre[2];
+    unsigned slot = 0, hslot = 0;
+    const int gstride = gridDim.x * NT;
+    const double tol = 1E-6, eps = 1E-12;
+    double a0 = 1E12, b0 = 1E12, p0 = 0.0, p1 = 0.0, pa = 0.0, pb = 0.0, pd = 1.0;
+    bool first = true;
+    int it = 0;
+    auto X = [&](int e) { return xs[e]; };
+    auto Y = [&](int e) { return ys[e]; };
+    double mn = INFINITY;
+    for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+        mn = fmin(mn, X(e));
+    for (; it < 10000; it++)
+    {
+        double q[5] = {0, 0, 0, 0, 0}, Q[5];
+        for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+        {
+            const double xe = X(e), ye = Y(e);
+            double w = 1.0;
+            if (!first)
+            {
+                const double r = fabs((ye - (xe * pa + pb)) / pd);
+                w = (r < 0.75) ? 1.0 : 0.75 / r;
+            }
+            const double w2 = w * w;
+            q[0] += w2;
+            q[1] += w2 * xe;
+            q[2] += w2 * ye;
+            q[3] += w2 * (xe * ye);
+            q[4] += w2 * (xe * xe);
+        }
+        grid_sum<NT, 5>(q, Q, grid, gs, slot, sm);
+        p0 = Q[0] * Q[3] - Q[1] * Q[2];
+        const double aux = Q[0] * Q[4] - Q[1] * Q[1];
+        p0 = (fabs(aux) < eps) ? a0 : p0 / aux;
+        p1 = Q[2] - p0 * Q[1];
+        p1 = (fabs(aux) < eps) ? b0 : p1 / Q[0];
+        double v1[1] = {0.0}, o1[1];
+        for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
+            v1[0] += fabs(Y(e) - (X(e) * p0 + p1));
+        grid_sum<NT, 1>(v1, o1, grid, gs, slot, sm);
+        const double ee = o1[0] / (double)n;
+        if ((fabs(a0 - p0) < tol && fabs(b0 - p1) < tol) || ee < tol)
+            break;
+        a0 = p0;
+        b0 = p1;
+        auto getR = [&](int e) { return Y(e) - (X(e) * p0 + p1); };
+        const int mq = (int)floor((floor((double)((n + 1) / 2)) + 1) / 2);
+        const double rhi = grid_select<NT>(getR, n, n - mq - 1, grid, gs, hslot, hist, spre);
+        const double rlo = grid_select<NT>(getR, n, mq - 1, grid, gs, hslot, hist, spre);
+        pd = (rhi - rlo) + eps;
+        pa = p0;
+        pb = p1;
+        first = false;
+    }
+    // smallest robust mean (robustMeans(0) after the sort, noise.hpp:141)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double r = sm[0];
+        for (int w = 1; w < NT / 32; w++)
+            r = fmin(r, sm[w]);
+        gs.partials[(size_t)(slot & 3u) * 8 * gridDim.x + blockIdx.x] = r;
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        double r = INFINITY;
+        for (unsigned b = 0; b < gridDim.x; b++)
+            r = fmin(r, gs.partials[(size_t)(slot & 3u) * 8 * gridDim.x + b]);
+        out[0] = p0;
+        out[1] = p1;
+        out[2] = (double)it;
+        out[3] = r;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+// Per-slice results are cached: a window slice is the frame divided by the window maximum, so its quadtree and its
+// (mean, variance) samples depend only on (global frame, uMax).  Consecutive windows share 2*fw of their slices and
+// very often the maximum, so in steady state one new slice is analysed per frame; the line fit always runs over
+// the samples of all slices of the window.
+struct NoiseSliceSamples
+{
+    double umax = 0;
+    std::vector<double> xs, ys; // robust means / variances in the reference's node order (duplicates included)
+};
+
+struct NoiseWorkspace
+{
+    unsigned char *dFlags = nullptr;
+    NoiseRegion *dRegions = nullptr;
+    int *dBig = nullptr;
+    double *dScratch = nullptr, *dLeaf = nullptr, *dFit = nullptr, *dPartials = nullptr, *dX = nullptr, *dY = nullptr;
+    unsigned *dHist = nullptr;
+    size_t capFlags = 0, capRegions = 0, capScratch = 0, capSamples = 0, capBig = 0;
+    int grid = 0;
+    long long n_split_calls = 0, n_regions = 0, n_samples = 0, n_big = 0, slices_analysed = 0, slices_reused = 0;
+    double fit_iters = 0;
+    std::unordered_map<long long, NoiseSliceSamples> cache;
+    void release()
+    {
+        auto F = [](void *p) {
+            if (p)
+                cudaFree(p);
+        };
+        F(dFlags), F(dRegions), F(dBig), F(dScratch), F(dLeaf), F(dFit), F(dPartials), F(dHist), F(dX), F(dY);
+        dFlags = nullptr, dRegions = nullptr, dBig = nullptr, dScratch = dLeaf = dFit = dPartials = dX = dY = nullptr, dHist = nullptr;
+        capFlags = capRegions = capScratch = capSamples = capBig = 0;
+        cache.clear();
+    }
+};
+
+static double noise_ftest0025(int s)
+{ // fTest0025 / degOfFreePlus1, noise.hpp:163-178
+    static const int dof[12] = {2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
+    static const double f[12] = {15.4392, 2.86209, 1.64602, 1.27893, 1.13046, 1.06318, 1.03110, 1.01543, 1.00769, 1.00384, 1.00192, 1.00096};
+    for (int i = 0; i < 12; i++)
+        if (dof[i] == s)
+            return f[i];
+    return -1.0;
+}
+
+#define NCU(call)                                                                                         \
+    do                                                                                                    \
+    {                                                                                                     \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+        {                                                                                                 \
+            char b_[256];                                                                                 \
+            snprintf(b_, sizeof b_, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            err = b_;                                                                                     \
+            return 2;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+
+#define NOISE_BIG_SIDE 128 /* regions with side >= this run grid-wide */
+
+static int noise_init(NoiseWorkspace &ws, int sm_count, std::string &err)
+{
+    if (ws.dFit)
+        return 0;
+    ws.grid = sm_count > 0 ? sm_count : 148;
+    NCU(cudaMalloc(&ws.dFit, 8 * sizeof(double)));
+    NCU(cudaMalloc(&ws.dPartials, (size_t)4 * 8 * ws.grid * sizeof(double)));
+    NCU(cudaMalloc(&ws.dHist, 4 * 256 * sizeof(unsigned)));
+    return 0;
+}
+
+// quadtree + leaf statistics of ONE slice (N x N doubles at dA) -> samples in the reference's order
+static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cudaStream_t st, NoiseSliceSamples &outS,
+                               long long *launches, std::string &err)
+{
+    // level table: sides N, N/2, ..., 8 (side 8 never splits but is needed to address regions)
+    std::vector<int> sides, offs;
+    int per_slice = 0, per_slice_flags = 0;
+    for (int s = N; s >= 8; s >>= 1)
+    {
+        sides.push_back(s);
+        offs.push_back(per_slice);
+        per_slice += (N / s) * (N / s);
+        if (s >= 16)
+            per_slice_flags = per_slice;
+    }
+    const size_t nflags = (size_t)per_slice_flags;
+    if (ws.capFlags < nflags)
+    {
+        if (ws.dFlags)
+            cudaFree(ws.dFlags);
+        NCU(cudaMalloc(&ws.dFlags, nflags));
+        ws.capFlags = nflags;
+    }
+    for (size_t l = 0; l < sides.size(); l++)
+    {
+        const int s = sides[l], nb = (N / s) * (N / s);
+        if (s < 16)
+            break;
+        const double ft = noise_ftest0025(s);
+        if (s >= 128)
+            k_noise_split<1024><<<dim3(nb, 1), 1024, 0, st>>>(dA, N, s, ft, ws.dFlags, per_slice_flags, offs[l]);
+        else
+            k_noise_split<128><<<dim3(nb, 1), 128, 0, st>>>(dA, N, s, ft, ws.dFlags, per_slice_flags, offs[l]);
+        if (launches)
+            (*launches)++;
+    }
+    std::vector<unsigned char> fl(nflags);
+    NCU(cudaMemcpyAsync(fl.data(), ws.dFlags, nflags, cudaMemcpyDeviceToHost, st));
+    NCU(cudaStreamSynchronize(st));
+
+    // replay QuadTree() (noise.hpp:419-458) against the decision table
+    struct Node
+    {
+        int i, j, s, lvl;
+    };
+    struct Frame
+    {
+        int n, k;
+    };
+    std::vector<NoiseRegion> regions;
+    std::vector<int> sample_region, big, region_of((size_t)per_slice, -1), dele;
+    std::vector<Node> tree;
+    std::vector<Frame> fr;
+    long long scratch_need = 0;
+    tree.push_back({0, 0, N, 0});
+    auto enter = [&](int part) {
+        const Node nd = tree[part];
+        ws.n_split_calls++;
+        if (nd.s <= 8)
+            return;
+        if (!fl[offs[nd.lvl] + (nd.i / nd.s) + (N / nd.s) * (nd.j / nd.s)])
+            return;
+        const int s = nd.s / 2;
+        const int n = (int)tree.size() - 1; // index of the LAST EXISTING node
+        tree.push_back({nd.i, nd.j, s, nd.lvl + 1});
+        tree.push_back({nd.i + s, nd.j, s, nd.lvl + 1});
+        tree.push_back({nd.i, nd.j + s, s, nd.lvl + 1});
+        tree.push_back({nd.i + s, nd.j + s, s, nd.lvl + 1});
+        dele.push_back(part);
+        fr.push_back({n, 0});
+    };
+    enter(0);
+    while (!fr.empty())
+    {
+        Frame &f = fr.back();
+        if (f.k == 4)
+        {
+            fr.pop_back();
+            continue;
+        }
+        const int part = f.n + f.k;
+        f.k++;
+        enter(part); // may push a new frame (f is not used afterwards)
+    }
+    std::sort(dele.begin(), dele.end());
+    dele.erase(std::unique(dele.begin(), dele.end()), dele.end());
+    std::vector<char> removed(tree.size(), 0);
+    for (size_t k = dele.size(); k-- > 1;) // k = size-1 … 1: the first entry (the root) is never shed
+        removed[dele[k]] = 1;
+    for (size_t n = 0; n < tree.size(); n++)
+    {
+        if (removed[n])
+            continue;
+        const Node &nd = tree[n];
+        int &ridx = region_of[offs[nd.lvl] + (nd.i / nd.s) + (N / nd.s) * (nd.j / nd.s)];
+        if (ridx < 0)
+        {
+            ridx = (int)regions.size();
+            regions.push_back({nd.i, nd.j, nd.s, 0, scratch_need});
+            scratch_need += (long long)nd.s * nd.s;
+            if (nd.s >= NOISE_BIG_SIDE)
+                big.push_back(ridx);
+        }
+        sample_region.push_back(ridx);
+    }
+    const size_t nreg = regions.size(), nbig = big.size();
+    ws.n_regions += (long long)nreg;
+    ws.n_samples += (long long)sample_region.size();
+    ws.n_big += (long long)nbig;
+    if (ws.capRegions < nreg)
+    {
+        if (ws.dRegions)
+            cudaFree(ws.dRegions);
+        if (ws.dLeaf)
+            cudaFree(ws.dLeaf);
+        NCU(cudaMalloc(&ws.dRegions, nreg * sizeof(NoiseRegion)));
+        NCU(cudaMalloc(&ws.dLeaf, nreg * 2 * sizeof(double)));
+        ws.capRegions = nreg;
+    }
+    if (ws.capScratch < (size_t)scratch_need)
+    {
+        if (ws.dScratch)
+            cudaFree(ws.dScratch);
+        NCU(cudaMalloc(&ws.dScratch, (size_t)scratch_need * sizeof(double)));
+        ws.capScratch = (size_t)scratch_need;
+    }
+    if (ws.capBig < nbig)
+    {
+        if (ws.dBig)
+            cudaFree(ws.dBig);
+        NCU(cudaMalloc(&ws.dBig, nbig * sizeof(int)));
+        ws.capBig = nbig;
+    }
+    NCU(cudaMemcpyAsync(ws.dRegions, regions.data(), nreg * sizeof(NoiseRegion), cudaMemcpyHostToDevice, st));
+    NCU(cudaMemcpyAsync(ws.dBig, big.data(), nbig * sizeof(int), cudaMemcpyHostToDevice, st));
+    // small regions: one CTA each (large ones return immediately inside the kernel)
+    k_noise_leaf<128><<<(unsigned)nreg, 128, 0, st>>>(dA, N, ws.dRegions, ws.dScratch, ws.dLeaf, NOISE_BIG_SIDE);
+    if (launches)
+        (*launches)++;
+    {
+        GridScratch gs;
+        gs.partials = ws.dPartials;
+        gs.ghist = ws.dHist;
+        gs.counters = nullptr;
+        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 256 * sizeof(unsigned), st));
+        const double *a0 = dA;
+        int a1 = N, a4 = (int)nbig;
+        const NoiseRegion *a2 = ws.dRegions;
+        const int *a3 = ws.dBig;
+        double *a5 = ws.dScratch, *a6 = ws.dLeaf;
+        void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
+        NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(ws.grid), dim3(512), args, 0, st));
+        if (launches)
+            (*launches)++;
+    }
+    std::vector<double> leaf(nreg * 2);
+    NCU(cudaMemcpyAsync(leaf.data(), ws.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCU(cudaStreamSynchronize(st));
+    NCU(cudaGetLastError());
+    outS.xs.clear();
+    outS.ys.clear();
+    outS.xs.reserve(sample_region.size());
+    outS.ys.reserve(sample_region.size());
+    for (int r : sample_region)
+    { // means and variances are filtered independently with >= 0 (noise.hpp:103-104)
+        const double mm = leaf[2 * (size_t)r], vv = leaf[2 * (size_t)r + 1];
+        if (mm >= 0.)
+            outS.xs.push_back(mm);
+        if (vv >= 0.)
+            outS.ys.push_back(vv);
+    }
+    return 0;
+}
+
+// Estimate (alpha, mu, sigma) of one window dU (N,N,T) whose slice k is global frame frame0+k divided by umax.
+// In/out values < 0 are estimated (noise.hpp:113-147).
+static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, int T, int method, int sm_count, cudaStream_t st,
+                                 double &alpha, double &mu, double &sigma, long long *launches, std::string &err,
+                                 long long frame0 = -1, double umax = 0.0)
+{
+    if (method != 4 && !(method < 1 || method > 4))
+    {
+        err = "noise_method 1-3 (mode-based estimates, noise.hpp:115-137) are not implemented on the GPU path; use noise_method=4";
+        return 3;
+    }
+    if (N < 16 || (N & (N - 1)) != 0 || N > 4096)
+    {
+        err = "quadtree noise estimation requires square frames with a power-of-two side between 16 and 4096";
+        return 1;
+    }
+    int rc = noise_init(ws, sm_count, err);
+    if (rc)
+        return rc;
+    std::vector<const NoiseSliceSamples *> parts(T);
+    std::vector<NoiseSliceSamples> local;
+    local.reserve(T);
+    if (frame0 >= 0)
+    { // drop cache entries that can no longer be part of a window
+        for (auto it = ws.cache.begin(); it != ws.cache.end();)
+            it = (it->first < frame0 - T || it->first > frame0 + 2 * T) ? ws.cache.erase(it) : std::next(it);
+    }
+    for (int k = 0; k < T; k++)
+    {
+        const double *dA = dU + (size_t)N * N * k;
+        if (frame0 >= 0)
+        {
+            NoiseSliceSamples &e = ws.cache[frame0 + k];
+            if (e.umax != umax || e.xs.empty())
+            {
+                e.umax = umax;
+                if ((rc = noise_analyse_slice(ws, dA, N, st, e, launches, err)))
+                    return rc;
+                ws.slices_analysed++;
+            }
+            else
+                ws.slices_reused++;
+            parts[k] = &e;
+        }
+        else
+        {
+            local.emplace_back();
+            if ((rc = noise_analyse_slice(ws, dA, N, st, local.back(), launches, err)))
+                return rc;
+            ws.slices_analysed++;
+            parts[k] = &local.back();
+        }
+    }
+    size_t n = 0, ny = 0;
+    for (int k = 0; k < T; k++)
+    {
+        n += parts[k]->xs.size();
+        ny += parts[k]->ys.size();
+    }
+    if (n != ny || n == 0)
+    {
+        err = "noise estimation produced a negative robust mean or variance (the reference's sample filtering would misalign)";
+        return 1;
+    }
+    std::vector<double> xs, ys;
+    xs.reserve(n);
+    ys.reserve(n);
+    for (int k = 0; k < T; k++)
+    {
+        xs.insert(xs.end(), parts[k]->xs.begin(), parts[k]->xs.end());
+        ys.insert(ys.end(), parts[k]->ys.begin(), parts[k]->ys.end());
+    }
+    if (ws.capSamples < n)
+    {
+        if (ws.dX)
+            cudaFree(ws.dX);
+        if (ws.dY)
+            cudaFree(ws.dY);
+        NCU(cudaMalloc(&ws.dX, n * sizeof(double)));
+        NCU(cudaMalloc(&ws.dY, n * sizeof(double)));
+        ws.capSamples = n;
+    }
+    NCU(cudaMemcpyAsync(ws.dX, xs.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NCU(cudaMemcpyAsync(ws.dY, ys.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        GridScratch gs;
+        gs.partials = ws.dPartials;
+        gs.ghist = ws.dHist;
+        gs.counters = nullptr;
+        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 256 * sizeof(unsigned), st));
+        const double *a0 = ws.dX, *a1 = ws.dY;
+        int a2 = (int)n;
+        double *a3 = ws.dFit;
+        void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&gs};
+        NCU(cudaLaunchCooperativeKernel((void *)k_noise_wls_grid<512>, dim3(ws.grid), dim3(512), args, 0, st));
+        if (launches)
+            (*launches)++;
+    }
+    double fit[4];
+    NCU(cudaMemcpyAsync(fit, ws.dFit, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCU(cudaStreamSynchronize(st));
+    NCU(cudaGetLastError());
+    ws.fit_iters = fit[2];
+    // noise.hpp:113,139-146 (method 4; the default branch is the same)
+    alpha = (alpha >= 0.) ? alpha : fit[0];
+    mu = (mu >= 0.) ? mu : fit[3];
+    sigma = (sigma >= 0.) ? sigma : std::sqrt(std::fabs(fit[1] + fit[0] * mu));
+    return 0;
+}
+#undef NCU
 } // namespace pgs

@@ -335,6 +335,7 @@ extern "C" int pguresvt_resident_range(const pguresvt_handle *h, uint32_t *first
 static int invalidate(pguresvt_handle *h)
 {
     h->uploaded = true;
+    h->noise_ws.cache.clear();
     h->prefiltered = false;
     h->cur_t = -1;
     h->cur_opt_ready = false;
@@ -837,7 +838,7 @@ static int estimate_noise(pguresvt_handle *h, double &alpha, double &mu, double 
         return PGS_OK;
     StageTimer tm(h, 8);
     return noise_estimate_window(h->noise_ws, h->dU, (int)h->N, (int)h->win, (int)h->p.noise_method, h->sm_count, h->st, alpha, mu,
-                                 sigma, &h->launches, g_err);
+                                 sigma, &h->launches, g_err, (long long)h->cur_a, h->cur_uMax);
 }
 
 static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.hpp:90-167
@@ -1139,7 +1140,7 @@ extern "C" int pguresvt_probe_noise(pguresvt_handle *h, uint32_t t, double *alph
     if ((rc = stage_window(h, t)))
         return rc;
     return noise_estimate_window(h->noise_ws, h->dU, (int)h->N, (int)h->win, (int)h->p.noise_method, h->sm_count, h->st, *alpha, *mu,
-                                 *sigma, &h->launches, g_err);
+                                 *sigma, &h->launches, g_err, (long long)h->cur_a, h->cur_uMax);
 }
 
 extern "C" int pguresvt_device_info(int device, char *name, int len)

@@ -357,3 +357,48 @@ def test_hyperspy_wrapper_with_duck_typed_signal():
     ref = SVT(optimize_pgure=False, lambda1=0.15).denoise(X).Y_
     assert out.data.shape == sig.data.shape and out.metadata.General.title == "Denoised stack"
     assert np.allclose(out.data, np.transpose(ref, (2, 0, 1)), rtol=1e-12, atol=1e-9)
+
+
+# ------------------------------------------------------------------ noise estimation (noise.hpp) on the GPU
+def test_noise_estimate_golden(golden):
+    X = golden["X"]
+    h = bridge.Handle(X, optimize_pgure=True, random_seed=1)
+    a, m, s = h.probe_noise(8)
+    assert np.allclose([a, m, s], golden["noise8"], rtol=1e-6, atol=0), (a, m, s, golden["noise8"])
+    # user-supplied values are kept, the others estimated (noise.hpp:113,141-145)
+    a2, m2, s2 = h.probe_noise(8, alpha=0.07, mu=-1.0, sigma=-1.0)
+    assert a2 == 0.07 and np.isclose(m2, golden["noise8"][1], rtol=1e-6)
+    h.close()
+
+
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_noise_estimate_vs_oracle(N):
+    X, _ = synthetic_sequence(N, 15, seed=N)
+    h = bridge.Handle(X, optimize_pgure=True, random_seed=1)
+    got = h.probe_noise(7)
+    u = X.astype(np.float64)
+    u /= u.max()
+    want = orc.noise_estimate(u, 4)[:3]
+    assert np.allclose(got, want, rtol=1e-6, atol=0), (got, want)
+    h.close()
+
+
+def test_default_api_estimates_noise(golden):
+    """SVT() with the reference's defaults: noise parameters unknown -> estimated per frame on the GPU."""
+    X = golden["X"]
+    s = SVT(random_seed=1).denoise(X)
+    ref, est = orc.pguresvt(X, optimize_pgure=True, lambda1=-1.0, random_seed=1)
+    assert np.allclose(s.noise_alphas_, est[:, 1], rtol=1e-6) and np.allclose(s.noise_mus_, est[:, 2], rtol=1e-6)
+    assert np.allclose(s.noise_sigmas_, est[:, 3], rtol=1e-6)
+    rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
+    assert rel.max() < LAM_TOL, rel
+    assert per_frame_rel_err(s.Y_, ref) < 1e-4
+
+
+def test_reference_default_test_on_gpu(ref_test_cube):
+    """test_svt.py:75-90 (default SVT, nsed < 0.025) through the GPU path."""
+    X, Y = ref_test_cube
+    s = SVT(n_jobs=1, random_seed=101).denoise(Y)
+    for a in ("Y_", "lambda1s_", "noise_alphas_", "noise_mus_", "noise_sigmas_"):
+        assert hasattr(s, a)
+    assert nsed(X, s.Y_) < 0.025
