@@ -402,3 +402,56 @@ def test_reference_default_test_on_gpu(ref_test_cube):
     for a in ("Y_", "lambda1s_", "noise_alphas_", "noise_mus_", "noise_sigmas_"):
         assert hasattr(s, a)
     assert nsed(X, s.Y_) < 0.025
+
+
+# ------------------------------------------------------------------ hot-pixel prefilter + CLI (configs 1-2)
+def test_hotpixel_vs_oracle():
+    import ctypes as C
+
+    # Under the uint16 modular arithmetic of SURVEY Q22 every pixel below the frame median wraps to a huge deviation,
+    # so the filter only fires when the median is the frame minimum: a flat background with sparse structure on top.
+    rng = np.random.RandomState(4)
+    X = np.full((64, 64, 6), 100, dtype=np.uint16, order="F")
+    for t in range(6):
+        sel = rng.rand(64, 64) < 0.3
+        X[:, :, t][sel] = rng.randint(101, 200, sel.sum())
+        rr, cc = rng.randint(0, 64, 40), rng.randint(0, 64, 40)
+        X[rr, cc, t] = 60000  # hot pixels, some adjacent, some on the edge (order-dependent replacement)
+        X[10, 10, t] = X[11, 10, t] = X[10, 11, t] = 65000
+        X[0, 5, t] = X[63, 63, t] = 64000
+    want = orc.hotpixel_u16(X, 10.0)
+    got = X.copy(order="F")
+    L = bridge.load()
+    bridge.check(L.pguresvt_hotpixel_u16(got.ctypes.data_as(C.POINTER(C.c_uint16)), 64, 64, 6, C.c_double(10.0), 0), "hotpixel")
+    assert (want != X).sum() > 100
+    assert np.array_equal(got, want)
+
+
+def test_cli_config1_example_tif(tmp_path):
+    """BASELINE configs[0]: examples/example.tif with param_example.svt through the PGURE-SVT CLI (frames 1-17 here to
+    keep the CPU oracle short): 128x128 uint16, patch 16 / overlap 2 (256x15 Casorati), fixed lambda 0.15,
+    exponential weighting, ARPS on, median radius 5."""
+    import shutil
+    import subprocess
+
+    import cv2
+
+    exe = os.path.join(os.path.dirname(bridge.lib_path()), "PGURE-SVT")
+    shutil.copy(os.path.join(GOLDEN, "example.tif"), tmp_path / "example.tif")
+    par = open(os.path.join(GOLDEN, "param_example.svt")).read().replace("end_frame   : 25", "end_frame   : 17")
+    (tmp_path / "p.svt").write_text(par)
+    r = subprocess.run([exe, "p.svt"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PGURE-SVT:" in r.stdout and "TIFF import:" in r.stdout
+    ok, pages = cv2.imreadmulti(str(tmp_path / "example-CLEANED.tif"), flags=cv2.IMREAD_UNCHANGED)
+    assert ok and len(pages) == 17 and pages[0].dtype == np.uint16
+    got = np.stack(pages, axis=2)  # (y, x, t) == cube(row, col, frame)
+    ok, inp = cv2.imreadmulti(os.path.join(GOLDEN, "example.tif"), flags=cv2.IMREAD_UNCHANGED)
+    X = np.asfortranarray(np.stack(inp[:17], axis=2))
+    ref, _ = orc.pguresvt(X, trajectory_length=15, patch_size=16, patch_overlap=2, motion_window=7, motion_filter=5,
+                          optimize_pgure=False, lambda1=0.15, exponential_weighting=True, motion_estimation=True,
+                          noise_alpha=0.1, noise_mu=0.1, noise_sigma=0.1, random_seed=1, max_iter=1000, n_jobs=-1)
+    want = np.where(ref < 0, 0, ref).astype(np.int64).astype(np.uint16)  # conv_to<uint16>: truncate, negatives -> 0
+    # truncation makes +-1 count differences possible where the double result sits within 1e-6 of an integer
+    diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-4
