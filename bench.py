@@ -268,7 +268,8 @@ def main():
 
     hbm, hbm_src, fp64, fp64_src = load_peaks()
     n = max(nst["n"], 1)
-    stage_ms = {k: acc.get(k, 0.0) / n for k in ("ms_median", "ms_arps", "ms_svd", "ms_search", "ms_final", "ms_noise", "ms_total")}
+    stage_ms = {k: acc.get(k, 0.0) / n for k in ("ms_median", "ms_arps", "ms_svd", "ms_search_prep", "ms_search", "ms_final",
+                                                   "ms_noise", "ms_total")}
     svds = acc.get("svds", 0.0) / n
     evals = acc.get("evals", 0.0) / n
     launches = acc.get("launches", 0.0) / n
@@ -279,20 +280,27 @@ def main():
     flops_per_launch = 77400.0 * (svds / svd_launches) if svd_launches else 0.0
     svd_ms_per_launch = stage_ms["ms_svd"] / svd_launches if svd_launches else 0.0
     achieved_tf = flops_per_launch / (svd_ms_per_launch * 1e-3) / 1e12 if svd_ms_per_launch > 0 else 0.0
-    roofline = {"kernel": "k_svd_16x15", "bound": "fp64", "achieved": achieved_tf, "peak": fp64, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64 if fp64 else None, "traffic": None,
+    roofline = {"kernel": "k_svd16_l4 (4-lane register Jacobi, 16x15)", "bound": "fp64", "achieved": achieved_tf, "peak": fp64,
+                "unit": "TFLOP/s", "frac": achieved_tf / fp64 if fp64 else None, "traffic": None,
                 "peak_source": fp64_src, "note": "FP64 vector-pipe bound (tensor cores not applicable); algorithmic "
-                "flops 14mn^2+8n^3 per SVD, CUDA-event time of the SVD stage / launches",
+                "flops 14mn^2+8n^3 = 77,400 per SVD x SVDs per launch / CUDA-event time of the SVD stage per launch; ncu "
+                "(profiles/) shows the FP64 pipe 59% busy on the cold kernel: one-sided Jacobi executes ~3.6x the algorithmic flops",
                 "share_of_step": stage_ms["ms_svd"] / stage_ms["ms_total"] if stage_ms["ms_total"] else None}
-    # secondary: lambda-search evaluations (HBM-bound): bytes = cached factors read per evaluation
-    fac_bytes = acc.get("factor_bytes", 0.0) / n
+    # secondary: one lambda-search evaluation (k_eval3 + k_risk_uhat).  Algorithmic bytes per evaluation: S and q of the
+    # three objects (768 B per patch) + the surviving singular triplets of object 0 (256 B each) + the 240-entry block
+    # overlap-added per patch (1,920 B of FP64 REDs) + one pass over the Uhat accumulator, weights and u (20 B / voxel).
     ev_per_frame = evals / fps_step if fps_step else 0
     search_ms_per_eval = stage_ms["ms_search"] / evals if evals else 0.0
-    ach_gbs = fac_bytes / (search_ms_per_eval * 1e-3) / 1e9 if search_ms_per_eval > 0 else 0.0
-    roofline2 = {"kernel": "k_recon+k_risk (one PGURE evaluation)", "bound": "hbm", "achieved": ach_gbs, "peak": hbm,
+    npatch = (size - 3) ** 2
+    trip = acc.get("eval_triplets", 0.0) / n
+    alg_bytes = (evals * (npatch * (768 + 1920) + size * size * 15 * 20) + trip * 256) / evals if evals else 0.0
+    ach_gbs = alg_bytes / (search_ms_per_eval * 1e-3) / 1e9 if search_ms_per_eval > 0 else 0.0
+    roofline2 = {"kernel": "k_eval3 + k_risk_uhat (one PGURE evaluation)", "bound": "hbm", "achieved": ach_gbs, "peak": hbm,
                  "unit": "GB/s", "frac": ach_gbs / hbm if hbm else None, "traffic": None, "peak_source": hbm_src,
-                 "note": "algorithmic bytes = SVD factor cache of the frame (all SVT objects) per evaluation",
-                 "evals_per_frame": ev_per_frame}
+                 "note": "algorithmic bytes = S+q of 3 objects + surviving triplets of object 0 + RED block + voxel pass; "
+                 "ncu: L2 (LTS) is the busiest unit (FP64 RED sector-ops), not DRAM",
+                 "evals_per_frame": ev_per_frame, "algorithmic_bytes_per_eval": alg_bytes,
+                 "triplets_per_patch_per_eval": trip / (evals * npatch) if evals else None}
     line = {"metric": "denoised frames/s (1024^2, PGURE lambda)" if not args.fixed_lambda else "denoised frames/s (fixed lambda)",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

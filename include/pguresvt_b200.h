@@ -125,8 +125,10 @@ int pguresvt_download(pguresvt_handle *h, double *Y_full, double *estimates_full
  *  [0] kernel launches   [1] patch SVDs computed   [2] PGURE objective evaluations
  *  [3] ms median   [4] ms ARPS   [5] ms SVD   [6] ms lambda search (reconstruct+risk)   [7] ms final reconstruct
  *  [8] ms noise estimation   [9] ms total (device timeline)   [10] SVD sweeps (sum over launches, max per launch)
- *  [11] bytes of SVD factors resident per frame */
-#define PGS_NSTATS 16
+ *  [11] bytes of SVD factors resident per frame   [12]/[13] mean Jacobi sweeps (object 0 / warm-started objects)
+ *  [14]/[15] ARPS frame pairs computed / reused from the cross-window cache
+ *  [16] singular triplets streamed by all evaluations   [17] ms search preparation (weights, multipliers, q-forms) */
+#define PGS_NSTATS 24
 int pguresvt_get_stats(const pguresvt_handle *h, double *stats);
 
 /* ---------------------------------------------------------------------------------------------

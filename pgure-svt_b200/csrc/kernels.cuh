@@ -245,8 +245,12 @@ __device__ __forceinline__ double arps_cost(const double *__restrict__ A1, const
 }
 
 #define ARPS_MAX_MW 15
-__global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw, int f1, int f2, int f3,
-                            short2 *__restrict__ pos, short2 *__restrict__ mot, int vecSize, double oobs2,
+// `pred` (optional) is the trajectory slice whose displacement from the grid position is this pair's predictor,
+// i.e. motions(:, it, f3) of the reference when an earlier pair of the same frame wrote it (only the first backward
+// pair, which reads what the first forward pair wrote: arps.hpp:68-77); NULL = zero predictor.
+// `out` is the trajectory slice of the target frame f2.
+__global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw, int f1, int f2,
+                            const short2 *__restrict__ pred, short2 *__restrict__ out, int vecSize, double oobs2,
                             unsigned long long *__restrict__ ncost)
 {
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +293,12 @@ __global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw,
     }
     else
     {
-        const short2 pm = mot[(size_t)f3 * vecSize + it];
+        short2 pm = make_short2(0, 0);
+        if (pred)
+        {
+            const short2 pp = pred[it];
+            pm = make_short2((short)(pp.x - i), (short)(pp.y - j));
+        }
         const int yTmp = abs((int)pm.x), xTmp = abs((int)pm.y);
         stepSize = (xTmp <= yTmp) ? yTmp : xTmp;
         if (((yTmp == 0) && (xTmp == stepSize)) || ((xTmp == 0) && (yTmp == stepSize)))
@@ -368,8 +377,7 @@ __global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw,
         }
         nSDSP++;
     } while (!done);
-    mot[(size_t)f3 * vecSize + it] = make_short2((short)(y - i), (short)(x - j));
-    pos[(size_t)f2 * vecSize + it] = make_short2((short)y, (short)x);
+    out[it] = make_short2((short)y, (short)x);
     if (ncost)
         atomicAdd(ncost, (unsigned long long)nc);
 #undef CHK_SET
@@ -849,6 +857,21 @@ __device__ __forceinline__ void tr4_16(const double (&x)[16], int sub, double (&
     }
 }
 
+// cp.async helpers (16-byte global -> shared copies that bypass L1; completion tracked per thread in groups)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NN>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
+}
+
+#define SVD16_V0_STRIDE 242 /* doubles per matrix in shared memory: 15 x 16 + 2 padding (bank spread) */
+
 template <int WARM>
 __global__ void __launch_bounds__(128, 2)
     k_svd16_l4(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
@@ -863,6 +886,19 @@ __global__ void __launch_bounds__(128, 2)
         pidx = P - 1;
     const int id = ids[pidx];
     const size_t fsz = (size_t)N * N;
+    extern __shared__ __align__(16) double sv0[]; // WARM: V of object 0 for the block's 32 matrices
+    if (WARM)
+    { // request V0 (15 columns x 16 doubles) of this lane's matrix now; it is consumed after the gather below
+        const double *V0g = fac0 + (size_t)SVD16_REC * pidx + SVD16_M * SVD16_N;
+        double *dst = sv0 + (size_t)(threadIdx.x >> 2) * SVD16_V0_STRIDE;
+#pragma unroll
+        for (int q = 0; q < 30; q++) // 120 16-byte pieces per matrix, 30 per lane
+        {
+            const int piece = q * 4 + sub;
+            cp_async16(dst + 2 * piece, V0g + 2 * piece);
+        }
+        cp_async_commit();
+    }
 
     // slot 0 is the fixed seat of the round-robin schedule: it holds the zero padding column, so slot pair 0 is a
     // no-op in every round and is skipped statically; real column k lives in slot k+1
@@ -884,7 +920,9 @@ __global__ void __launch_bounds__(128, 2)
     { // rows of A times V0 (column-major, ld 16): each row independently; the 15 results of a row are parked in a
       // lane-private shared-memory column so that the register file never holds two copies of the matrix
         __shared__ double stage[SVD16_N][128];
-        const double *V0 = fac0 + (size_t)SVD16_REC * pidx + SVD16_M * SVD16_N;
+        cp_async_wait<0>();
+        __syncwarp();
+        const double *V0 = sv0 + (size_t)(threadIdx.x >> 2) * SVD16_V0_STRIDE;
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
@@ -1136,37 +1174,85 @@ __device__ __forceinline__ double soft_f(double s, double smax, double lambda, i
     return fmax(s - w, 0.0); // s >= 0 from the Jacobi kernels
 }
 
-// cp.async helpers (16-byte global -> shared copies that bypass L1; completion tracked per thread in groups)
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+#define EV_C 3                  /* singular triplets of object 0 staged per chunk */
+#define EV_CH (EV_C * 32)       /* doubles per chunk: C columns x (16 of U | 16 of V) */
+#define EV_GRP (96 + 2 * EV_CH) /* doubles of shared memory per patch: S and q of 3 objects | two chunk buffers */
+
+// c4 = delta2 / weights (0 where no patch covers the voxel: svt.hpp:163-164 sets those voxels to 0), once per frame
+__global__ void k_c4(const unsigned *__restrict__ cnt, const int8_t *__restrict__ d2neg, double dNeg, double dPos, size_t n,
+                     double *__restrict__ c4)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NN>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        c4[i] = cnt[i] ? (d2neg[i] ? dNeg : dPos) / (double)cnt[i] : 0.0;
 }
 
-#define EV_C 3                      /* singular triplets staged per chunk */
-#define EV_CH (3 * EV_C * 32)       /* doubles per chunk: 3 objects x C columns x (16 of U | 16 of V) */
-#define EV_GRP (48 + 2 * EV_CH)     /* doubles of shared memory per patch: S of 3 objects | two chunk buffers */
+// K_qform — once per frame and SVT object: q[patch][k] = u_k^T C4_patch v_k, where C4_patch is the per-voxel
+// multiplier delta2 / weights gathered along the patch trajectory (a 16 x 15 matrix).  The second-difference term of
+// the risk,  s4 = sum_voxels delta2 (U2p - 2 Uhat + U2m)  (pgure.hpp:136), is LINEAR in the reconstructed blocks
+// b = sum_k f_k(lambda) u_k v_k^T, so for every lambda it collapses to  sum_patches sum_k f_k q_k  — the perturbed
+// objects never have to be rebuilt or overlap-added during the lambda search, only thresholded.
+// 16 lanes per patch, lane g = block row g.  q: 16 doubles per patch (slot 15 unused).
+__global__ void __launch_bounds__(128)
+    k_qform(const double *__restrict__ fac, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
+            const double *__restrict__ c4, double *__restrict__ q)
+{
+    const int g = threadIdx.x & 15;
+    int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const double *R = fac + (size_t)SVD16_REC * pidx;
+    const int id = ids[pidx];
+    const int r = g & 3, c = g >> 2;
+    const int fsz = N * N;
+    double cw[SVD16_N];
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        cw[k] = c4[(p.x + r) + N * (p.y + c) + fsz * k];
+    }
+    double mine = 0.0;
+#pragma unroll 1
+    for (int kk = 0; kk < SVD16_N; kk++)
+    {
+        const double2 *v = reinterpret_cast<const double2 *>(R + SVD16_M * SVD16_N + SVD16_LDV * kk);
+        double z = 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++)
+        {
+            const double2 x = v[k2];
+            z = fma(cw[2 * k2], x.x, z);
+            if (2 * k2 + 1 < SVD16_N)
+                z = fma(cw[2 * k2 + 1], x.y, z);
+        }
+        double val = R[SVD16_M * kk + g] * z;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+            val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (g == kk)
+            mine = val;
+    }
+    if (valid)
+        q[(size_t)16 * pidx + g] = mine;
+}
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
+            const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
-            double *__restrict__ acc0, double *__restrict__ accT)
+            double *__restrict__ acc0, double *__restrict__ partial, unsigned long long *__restrict__ ktot)
 {
-    // 16 lanes per patch; lane g owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices.
-    // The factor records are streamed through shared memory with 16-byte cp.async copies: the singular values of
-    // the three objects and the first EV_C singular triplets are requested up front (before anything depends on
-    // them), further chunks of EV_C triplets are double-buffered behind the arithmetic.  Singular values are sorted
-    // descending and the soft threshold is monotone, so the surviving triplets are a prefix: nothing beyond the
-    // largest surviving index is ever fetched.  Two accumulators per entry: a0 = block of Uhat, t = b2p + b2m - 2 b0
-    // (the second difference the risk needs, linear in the blocks); both are overlap-added with fire-and-forget
-    // FP64 REDs — per slice the 16 lanes cover the patch's 4 x 4 footprint.
+    // One PGURE evaluation for 16 x 15 patches and the three SVT objects U, U +- eps2*delta2.  16 lanes per patch; lane g
+    // owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices and thresholds slot g of every object.
+    //  * s4 (second difference) needs no block at all: sum_k (f2p_k q2p_k + f2m_k q2m_k - 2 f0_k q0_k), see k_qform.
+    //  * Uhat enters the risk non-linearly, so object 0's block is rebuilt (rank-adaptively: singular values are sorted
+    //    and the soft threshold is monotone, so the survivors are a prefix) and overlap-added with fire-and-forget
+    //    FP64 REDs — per slice the 16 lanes cover the patch's 4 x 4 footprint.
+    // Factor data is streamed through shared memory with 16-byte cp.async copies: S and q of the three objects and
+    // the first EV_C triplets of object 0 are requested before anything depends on them, further chunks are
+    // double-buffered behind the arithmetic.
     __shared__ __align__(16) double smem[8 * EV_GRP];
     const int lane = threadIdx.x & 31;
     const int g = threadIdx.x & 15;
@@ -1176,34 +1262,37 @@ __global__ void __launch_bounds__(128, MINB)
     if (!valid)
         pidx = P - 1;
     const size_t roff = (size_t)SVD16_REC * pidx;
-    const double *R[3] = {fac0 + roff, fac2 + roff, fac3 + roff};
+    const double *R0 = fac0 + roff;
     const int soff = SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
-    // ---- requests: S (lanes 0..7 copy 16 bytes of each object's S), chunk 0
     if (g < 8)
-    {
-#pragma unroll
-        for (int o = 0; o < 3; o++)
-            cp_async16(sg + 16 * o + 2 * g, R[o] + soff + 2 * g);
+    { // S of the three objects
+        cp_async16(sg + 0 + 2 * g, fac0 + roff + soff + 2 * g);
+        cp_async16(sg + 16 + 2 * g, fac2 + roff + soff + 2 * g);
+        cp_async16(sg + 32 + 2 * g, fac3 + roff + soff + 2 * g);
+    }
+    else
+    { // q of the three objects
+        const int h2 = 2 * (g - 8);
+        cp_async16(sg + 48 + h2, q0 + (size_t)16 * pidx + h2);
+        cp_async16(sg + 64 + h2, q2 + (size_t)16 * pidx + h2);
+        cp_async16(sg + 80 + h2, q3 + (size_t)16 * pidx + h2);
     }
     auto request_chunk = [&](int c0, int buf) {
-        double *dst = sg + 48 + buf * EV_CH;
+        double *dst = sg + 96 + buf * EV_CH;
 #pragma unroll
-        for (int o = 0; o < 3; o++)
-#pragma unroll
-            for (int c = 0; c < EV_C; c++)
+        for (int c = 0; c < EV_C; c++)
+        {
+            const int kk = c0 + c;
+            if (kk < SVD16_N)
             {
-                const int kk = c0 + c;
-                if (kk < SVD16_N)
-                {
-                    // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
-                    const double *src = (g < 8) ? R[o] + SVD16_M * kk + 2 * g : R[o] + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
-                    cp_async16(dst + (o * EV_C + c) * 32 + 2 * g, src);
-                }
+                // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
+                const double *src = (g < 8) ? R0 + SVD16_M * kk + 2 * g : R0 + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
+                cp_async16(dst + c * 32 + 2 * g, src);
             }
+        }
     };
     request_chunk(0, 0);
     cp_async_commit();
-    // trajectory (independent of the factor data)
     const int id = ids[pidx];
     const int r = g & 3, c = g >> 2;
     const int fsz = N * N;
@@ -1216,55 +1305,45 @@ __global__ void __launch_bounds__(128, MINB)
     }
     cp_async_wait<0>();
     __syncwarp();
-    // ---- thresholds: lane g handles slot g of each object
-    double f0, f2, f3;
+    double f0 = 0.0, s4 = 0.0;
+    if (g < SVD16_N)
     {
-        const double sm0 = sg[15], sm2 = sg[16 + 15], sm3 = sg[32 + 15];
-        f0 = (g < SVD16_N) ? soft_f(sg[g], sm0, lambda, expw) : 0.0;
-        f2 = (g < SVD16_N) ? soft_f(sg[16 + g], sm2, lambda, expw) : 0.0;
-        f3 = (g < SVD16_N) ? soft_f(sg[32 + g], sm3, lambda, expw) : 0.0;
+        f0 = soft_f(sg[g], sg[15], lambda, expw);
+        const double f2 = soft_f(sg[16 + g], sg[16 + 15], lambda, expw);
+        const double f3 = soft_f(sg[32 + g], sg[32 + 15], lambda, expw);
+        s4 = fma(f2, sg[64 + g], fma(f3, sg[80 + g], -2.0 * f0 * sg[48 + g]));
     }
-    unsigned m = __ballot_sync(0xffffffffu, (f0 != 0.0) || (f2 != 0.0) || (f3 != 0.0));
+    unsigned m = __ballot_sync(0xffffffffu, f0 != 0.0);
     m = (m | (m >> 16)) & 0xffffu;
     const int Kw = 32 - __clz(m); // one past the largest surviving index over both patches of the warp (0 if none)
-    double a0[SVD16_N], t[SVD16_N];
+    double a0[SVD16_N];
 #pragma unroll
     for (int k = 0; k < SVD16_N; k++)
-        a0[k] = t[k] = 0.0;
+        a0[k] = 0.0;
     int buf = 0;
     for (int c0 = 0; c0 < Kw; c0 += EV_C)
     {
         if (c0 + EV_C < Kw)
             request_chunk(c0 + EV_C, buf ^ 1);
         cp_async_commit();
-        const double *cb = sg + 48 + buf * EV_CH;
+        const double *cb = sg + 96 + buf * EV_CH;
 #pragma unroll
         for (int cc = 0; cc < EV_C; cc++)
         {
             const int kk = c0 + cc;
             if (kk < Kw)
             {
-                const int src = (lane & 16) | kk;
-                const double fk0 = __shfl_sync(0xffffffffu, f0, src);
-                const double fk2 = __shfl_sync(0xffffffffu, f2, src);
-                const double fk3 = __shfl_sync(0xffffffffu, f3, src);
-                const double *b0 = cb + (0 * EV_C + cc) * 32, *b2 = cb + (1 * EV_C + cc) * 32, *b3 = cb + (2 * EV_C + cc) * 32;
-                const double u0 = b0[g] * fk0, u2 = b2[g] * fk2, u3 = b3[g] * fk3;
-                const double um = -2.0 * u0;
+                const double fk0 = __shfl_sync(0xffffffffu, f0, (lane & 16) | kk);
+                const double *b0 = cb + cc * 32;
+                const double u0 = b0[g] * fk0;
                 const double2 *v0 = reinterpret_cast<const double2 *>(b0 + 16);
-                const double2 *v2 = reinterpret_cast<const double2 *>(b2 + 16);
-                const double2 *v3 = reinterpret_cast<const double2 *>(b3 + 16);
 #pragma unroll
                 for (int k2 = 0; k2 < 8; k2++)
                 {
-                    const double2 x0 = v0[k2], x2 = v2[k2], x3 = v3[k2];
+                    const double2 x0 = v0[k2];
                     a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
-                    t[2 * k2] = fma(um, x0.x, fma(u2, x2.x, fma(u3, x3.x, t[2 * k2])));
                     if (2 * k2 + 1 < SVD16_N)
-                    {
                         a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
-                        t[2 * k2 + 1] = fma(um, x0.y, fma(u2, x2.y, fma(u3, x3.y, t[2 * k2 + 1])));
-                    }
                 }
             }
         }
@@ -1276,50 +1355,57 @@ __global__ void __launch_bounds__(128, MINB)
     {
 #pragma unroll
         for (int k = 0; k < SVD16_N; k++)
-        {
             atomicAdd(acc0 + vox[k], a0[k]);
-            atomicAdd(accT + vox[k], t[k]);
-        }
+    }
+    else
+        s4 = 0.0;
+    s4 = warp_sum(s4);
+    __shared__ double sm4[4];
+    __shared__ int smk[4];
+    if (lane == 0)
+    {
+        sm4[threadIdx.x >> 5] = s4;
+        smk[threadIdx.x >> 5] = 2 * Kw; // triplets of object 0 fetched for the warp's two patches (upper bound per patch)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        partial[blockIdx.x] = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
+        atomicAdd(ktot, (unsigned long long)(smk[0] + smk[1] + smk[2] + smk[3]));
     }
 }
 
 // voxel pass of the fused evaluation: Uhat = acc0 / weights (non-finite -> 0, svt.hpp:163-164);
-// s1 = sum (Uhat - U)^2, s5 = sum Uhat, s4 = sum delta2 * (accT / weights)   [accT = U2p + U2m - 2 Uhat, unnormalised]
-// partial: gridDim.x * 3 doubles
+// s1 = sum (Uhat - U)^2, s5 = sum Uhat.  partial: gridDim.x * 2 doubles
 __global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, const double *__restrict__ acc0,
-                            const double *__restrict__ accT, const int8_t *__restrict__ d2neg, double dNeg, double dPos, size_t tot,
-                            double *__restrict__ partial)
+                            size_t tot, double *__restrict__ partial)
 {
-    double s1 = 0, s5 = 0, s4 = 0;
+    double s1 = 0, s5 = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
-        const unsigned c = cnt[i];
-        const double v0 = norm_or_zero(acc0[i], c);
+        const double v0 = norm_or_zero(acc0[i], cnt[i]);
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
         s5 += v0;
-        s4 = fma(d2neg[i] ? dNeg : dPos, norm_or_zero(accT[i], c), s4);
     }
-    __shared__ double sm[3][32];
+    __shared__ double sm[2][32];
     s1 = warp_sum(s1);
     s5 = warp_sum(s5);
-    s4 = warp_sum(s4);
     if ((threadIdx.x & 31) == 0)
     {
         sm[0][threadIdx.x >> 5] = s1;
         sm[1][threadIdx.x >> 5] = s5;
-        sm[2][threadIdx.x >> 5] = s4;
     }
     __syncthreads();
     if (threadIdx.x < 32)
     {
 #pragma unroll
-        for (int q = 0; q < 3; q++)
+        for (int q = 0; q < 2; q++)
         {
             double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
             r = warp_sum(r);
             if (threadIdx.x == 0)
-                partial[(size_t)blockIdx.x * 3 + q] = r;
+                partial[(size_t)blockIdx.x * 2 + q] = r;
         }
     }
 }

@@ -77,13 +77,20 @@ struct pguresvt_handle
     void *dX = nullptr;
     uint16_t *dZ = nullptr, *dTmp16 = nullptr;
     double *dU = nullptr, *dW = nullptr;
-    short2 *dPos = nullptr, *dMot = nullptr;
+    short2 *dPos = nullptr, *dArpsF = nullptr, *dArpsB = nullptr;
+    struct ArpsTag
+    {
+        long long frame = -1;
+        double wmax = 0;
+    };
+    std::vector<ArpsTag> tagF, tagB;
+    int arps_ring = 0;
     int *dIds = nullptr;
     unsigned *dCnt = nullptr;
     double *dAcc[4] = {nullptr, nullptr, nullptr, nullptr};
     double *dFac[4] = {nullptr, nullptr, nullptr, nullptr};
     int8_t *dD1 = nullptr, *dD2 = nullptr;
-    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dAccT = nullptr;
+    double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dC4 = nullptr, *dPartialE = nullptr, *dQ[3] = {nullptr, nullptr, nullptr};
     double *dY = nullptr, *dEst = nullptr, *dV = nullptr;
     int *dSweeps = nullptr;
     unsigned long long *dNcost = nullptr;
@@ -140,10 +147,10 @@ static void free_all(pguresvt_handle *h)
         if (p)
             cudaFree(p);
     };
-    F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dMot), F(h->dIds), F(h->dCnt);
+    F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
-    F(h->dD1), F(h->dD2), F(h->dAccT), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
+    F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
     h->noise_ws.release();
     if (h->hOut)
@@ -250,7 +257,14 @@ static int create_impl(pguresvt_handle *h)
     if (p.motion_estimation)
         CU(cudaMalloc(&h->dW, wtot * sizeof(double)));
     CU(cudaMalloc(&h->dPos, (size_t)h->win * h->vecSize * sizeof(short2)));
-    CU(cudaMalloc(&h->dMot, (size_t)h->win * h->vecSize * sizeof(short2)));
+    if (p.motion_estimation)
+    {
+        h->arps_ring = (int)h->win + 2;
+        CU(cudaMalloc(&h->dArpsF, (size_t)h->arps_ring * h->vecSize * sizeof(short2)));
+        CU(cudaMalloc(&h->dArpsB, (size_t)h->arps_ring * h->vecSize * sizeof(short2)));
+        h->tagF.assign(h->arps_ring, pguresvt_handle::ArpsTag());
+        h->tagB.assign(h->arps_ring, pguresvt_handle::ArpsTag());
+    }
     CU(cudaMalloc(&h->dIds, (size_t)h->P * sizeof(int)));
     CU(cudaMemcpy(h->dIds, ids.data(), (size_t)h->P * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->dCnt, wtot * sizeof(unsigned)));
@@ -272,7 +286,10 @@ static int create_impl(pguresvt_handle *h)
         h->eval_blocks = cdiv((long long)h->P * 16, 128);
         if (wtot >= ((size_t)1 << 31))
             return fail(PGS_ERR_UNSUPPORTED, "window of %zu voxels exceeds the fused evaluation kernel's 32-bit indexing", wtot);
-        CU(cudaMalloc(&h->dAccT, wtot * sizeof(double)));
+        CU(cudaMalloc(&h->dC4, wtot * sizeof(double)));
+        CU(cudaMalloc(&h->dPartialE, (size_t)h->eval_blocks * sizeof(double)));
+        for (int k = 0; k < 3; k++)
+            CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
     }
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
@@ -336,6 +353,10 @@ static int invalidate(pguresvt_handle *h)
 {
     h->uploaded = true;
     h->noise_ws.cache.clear();
+    for (auto &tg : h->tagF)
+        tg.frame = -1;
+    for (auto &tg : h->tagB)
+        tg.frame = -1;
     h->prefiltered = false;
     h->cur_t = -1;
     h->cur_opt_ready = false;
@@ -539,61 +560,90 @@ static int stage_window(pguresvt_handle *h, uint32_t t)
     return PGS_OK;
 }
 
-static void arps_pair(pguresvt_handle *h, int f1, int f2, int f3)
+static void arps_pair(pguresvt_handle *h, int f1, int f2, const short2 *pred, short2 *out)
 {
     const double oobs2 = 1.0 / (double)(h->p.block_size * h->p.block_size);
-    k_arps_pair<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.block_size, h->p.motion_window, f1, f2, f3,
-                                                          h->dPos, h->dMot, h->vecSize, oobs2, h->dNcost);
+    k_arps_pair<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.block_size, h->p.motion_window, f1, f2, pred, out,
+                                                          h->vecSize, oobs2, h->dNcost);
     LAUNCHED(h);
+    h->stats[14] += 1;
+}
+
+// Trajectory slice of a zero-predictor pair, shared between windows: the search for (source frame -> target frame)
+// is independent of the output frame it is run for, as long as the window normalisation wMax is bit-identical
+// (the block cost is evaluated on w = z / wMax, and ties decide vectors).  Forward results are keyed by the target
+// frame g (source g-1), backward results by target g (source g+1).
+static int arps_cached_pair(pguresvt_handle *h, bool forward, int src_local, int tgt_local)
+{
+    const long long g = (long long)h->cur_a + tgt_local;
+    const int slot = (int)(g % h->arps_ring);
+    pguresvt_handle::ArpsTag &tag = forward ? h->tagF[slot] : h->tagB[slot];
+    short2 *cache = (forward ? h->dArpsF : h->dArpsB) + (size_t)slot * h->vecSize;
+    short2 *dst = h->dPos + (size_t)tgt_local * h->vecSize;
+    if (tag.frame == g && tag.wmax == h->cur_wMax)
+    {
+        CU(cudaMemcpyAsync(dst, cache, (size_t)h->vecSize * sizeof(short2), cudaMemcpyDeviceToDevice, h->st));
+        h->stats[15] += 1;
+        return PGS_OK;
+    }
+    arps_pair(h, src_local, tgt_local, nullptr, dst);
+    CU(cudaMemcpyAsync(cache, dst, (size_t)h->vecSize * sizeof(short2), cudaMemcpyDeviceToDevice, h->st));
+    tag.frame = g;
+    tag.wmax = h->cur_wMax;
+    return PGS_OK;
 }
 
 static int stage_motion(pguresvt_handle *h, uint32_t t) // MotionEstimator::Estimate, arps.hpp:52-134
 {
     const int tw = (int)h->fw, Ntw = (int)h->win, nImages = (int)h->nframes, ti = (int)t;
-    CU(cudaMemsetAsync(h->dPos, 0, (size_t)h->win * h->vecSize * sizeof(short2), h->st));
-    CU(cudaMemsetAsync(h->dMot, 0, (size_t)h->win * h->vecSize * sizeof(short2), h->st));
+    const int ref = h->cur_ref;
     CU(cudaMemsetAsync(h->dNcost, 0, sizeof(unsigned long long), h->st));
-    k_seed_pos<<<cdiv(h->vecSize, 256), 256, 0, h->st>>>(h->dPos, h->vecSize, h->M1, h->cur_ref);
-    LAUNCHED(h);
-    if (h->p.motion_estimation)
-    {
-        if (ti < tw)
-        {
-            const int loopEnd = Ntw - ti - 1;
-            for (int i = 0; i < loopEnd; i++)
-                arps_pair(h, ti + i, ti + i + 1, ti + i);
-            for (int i = 0; i < ti; i++)
-            {
-                const int negInc = -1 * (i + 1);
-                arps_pair(h, ti + negInc + 1, ti + negInc, ti + negInc + 1);
-            }
-        }
-        else if (ti >= nImages - tw)
-        {
-            const int endFrame = ti - (nImages - Ntw);
-            const int loopEnd = 2 * tw - endFrame;
-            for (int i = 0; i < loopEnd; i++)
-                arps_pair(h, endFrame + i, endFrame + i + 1, endFrame + i);
-            for (int i = 0; i < endFrame; i++)
-            {
-                const int negInc = -1 * (i + 1);
-                if (2 * tw == endFrame)
-                    arps_pair(h, endFrame + negInc + 1, endFrame + negInc, endFrame + negInc);
-                else
-                    arps_pair(h, endFrame + negInc + 1, endFrame + negInc, endFrame + negInc + 1);
-            }
-        }
-        else
-        {
-            for (int i = 0; i < tw; i++)
-                arps_pair(h, tw + i, tw + i + 1, tw + i);
-            for (int i = 0; i < tw; i++)
-            {
-                const int negInc = -1 * (i + 1);
-                arps_pair(h, tw + negInc + 1, tw + negInc, tw + negInc + 1);
-            }
-        }
+    if (!h->p.motion_estimation)
+    { // only the reference slice is populated; every other slice stays (0,0)
+        CU(cudaMemsetAsync(h->dPos, 0, (size_t)h->win * h->vecSize * sizeof(short2), h->st));
+        k_seed_pos<<<cdiv(h->vecSize, 256), 256, 0, h->st>>>(h->dPos, h->vecSize, h->M1, ref);
+        LAUNCHED(h);
+        CU(cudaGetLastError());
+        return PGS_OK;
     }
+    k_seed_pos<<<cdiv(h->vecSize, 256), 256, 0, h->st>>>(h->dPos, h->vecSize, h->M1, ref);
+    LAUNCHED(h);
+    // schedule of arps.hpp:54-133: nfwd forward pairs (ref+i -> ref+i+1), nbwd backward pairs (ref-i -> ref-i-1)
+    int nfwd, nbwd;
+    bool special = false; // last frame: the backward pairs read motion slots nobody wrote (arps.hpp:101-104)
+    if (ti < tw)
+    {
+        nfwd = Ntw - ti - 1;
+        nbwd = ti;
+    }
+    else if (ti >= nImages - tw)
+    {
+        const int endFrame = ti - (nImages - Ntw);
+        nfwd = 2 * tw - endFrame;
+        nbwd = endFrame;
+        special = (2 * tw == endFrame);
+    }
+    else
+    {
+        nfwd = tw;
+        nbwd = tw;
+    }
+    int rc;
+    for (int i = 0; i < nfwd; i++)
+        if ((rc = arps_cached_pair(h, true, ref + i, ref + i + 1)))
+            return rc;
+    for (int i = 0; i < nbwd; i++)
+    {
+        if (i == 0 && nfwd > 0 && !special)
+            // predictor = the vector the first forward pair found for the same block; specific to this frame
+            arps_pair(h, ref, ref - 1, h->dPos + (size_t)(ref + 1) * h->vecSize, h->dPos + (size_t)(ref - 1) * h->vecSize);
+        else if ((rc = arps_cached_pair(h, false, ref - i, ref - i - 1)))
+            return rc;
+    }
+    // slices no pair targets stay (0,0) like the zero-initialised icube (arps.hpp:42); with a full schedule none is left
+    for (int k = 0; k < Ntw; k++)
+        if (k > ref + nfwd || k < ref - nbwd)
+            CU(cudaMemsetAsync(h->dPos + (size_t)k * h->vecSize, 0, (size_t)h->vecSize * sizeof(short2), h->st));
     CU(cudaGetLastError());
     return PGS_OK;
 }
@@ -618,8 +668,17 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
             k_svd16_l4<0><<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
                                                                   nullptr, max_sweeps, tol2, big2, h->dSweeps);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
-            k_svd16_l4<1><<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
+        {
+            static bool attr_set = false;
+            const int smem_warm = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
+            if (!attr_set)
+            {
+                CU(cudaFuncSetAttribute(k_svd16_l4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
+                attr_set = true;
+            }
+            k_svd16_l4<1><<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
                                                                   h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
+        }
     }
     else if (h->use_reg_svd)
     {
@@ -693,21 +752,14 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
 {
     const size_t wtot = h->fsz * h->win;
     CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
-    CU(cudaMemsetAsync(h->dAccT, 0, wtot * sizeof(double), h->st));
-    static const int minb = getenv("PGURESVT_EVAL_MINB") ? atoi(getenv("PGURESVT_EVAL_MINB")) : 4;
-    if (minb == 3)
-        k_eval3<3><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
-                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
-    else if (minb == 5)
-        k_eval3<5><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
-                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
-    else
-        k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
-                                                      lambda, h->p.exp_weighting, h->dAcc[0], h->dAccT);
+    k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds,
+                                                  h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dNcost);
     LAUNCHED(h);
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], h->dAccT, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dPartial);
+    k_reduce_partials<<<1, 1024, 0, h->st>>>(h->dPartialE, h->eval_blocks, 1, h->dOut + 2);
     LAUNCHED(h);
-    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartial);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 2, h->dOut);
     LAUNCHED(h);
     CU(cudaMemcpyAsync(h->hOut, h->dOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
@@ -821,8 +873,21 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     }
     if (h->p.optimize_pgure)
     {
+        StageTimer tm(h, 17);
         if ((rc = stage_count(h, -1)))
             return rc;
+        if (h->use_fused_eval)
+        { // per-voxel multiplier delta2/weights, then the bilinear forms q = u^T C4 v of every triplet (see k_qform)
+            const size_t wtot = h->fsz * h->win;
+            k_c4<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dC4);
+            LAUNCHED(h);
+            const int objs3[3] = {0, 2, 3};
+            for (int k = 0; k < 3; k++)
+            {
+                k_qform<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[objs3[k]], h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dC4, h->dQ[k]);
+                LAUNCHED(h);
+            }
+        }
         if ((rc = sum_u(h, &h->cur_sumU)))
             return rc;
     }
@@ -856,6 +921,7 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
         if ((rc = estimate_noise(h, alpha, mu, sigma)))
             return rc;
         StageTimer tm(h, 6);
+        CU(cudaMemsetAsync(h->dNcost, 0, sizeof(unsigned long long), h->st));
         const double OoNxNyNt = 1.0 / ((double)h->N * h->N * h->Nt); // pguresvt.hpp:60 (the driver's Nt)
         double start = (lambda >= 0.0) ? lambda : h->cur_sumU * OoNxNyNt;
         start = std::max(0.0, start);
@@ -884,6 +950,13 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
             return fail(PGS_ERR_OPT,
                         "lambda search cannot start from %g (zero initial step; the reference's NLopt call throws here)", start);
         lambda = last; // the LAST evaluated lambda, not the optimum (pgure.hpp:128,236)
+        if (h->use_fused_eval)
+        { // singular triplets streamed by the evaluations of this frame (algorithmic-bytes accounting for bench.py)
+            unsigned long long kt = 0;
+            CU(cudaMemcpyAsync(&kt, h->dNcost, sizeof(kt), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            h->stats[16] += (double)kt;
+        }
     }
     {
         StageTimer tm(h, 7);
