@@ -384,6 +384,201 @@ __global__ void k_arps_pair(const double *__restrict__ w, int N, int bs, int mw,
 #undef CHK_GET
 }
 
+// K_arps, patch size 4 — same search, specialised: the 4x4 reference block lives in registers (it is compared against
+// ~16 candidate blocks), the visited-positions matrix is a 4 x 64-bit register bitmap, and the cost loop is fully
+// unrolled in the reference's accumulation order (even/odd column-major linear index -> two accumulators).
+__device__ __forceinline__ double arps_cost4(const double (&ref)[16], const double *__restrict__ A2, int N, int py, int px,
+                                             double oobs2)
+{
+    double v1 = 0.0, v2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+    {
+        const double *b = A2 + py + (size_t)N * (px + c);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            const double d = __dsub_rn(ref[4 * c + r], b[r]);
+            const double sq = __dmul_rn(d, d);
+            if ((4 * c + r) & 1)
+                v2 = __dadd_rn(v2, sq);
+            else
+                v1 = __dadd_rn(v1, sq);
+        }
+    }
+    return __dmul_rn(__dadd_rn(v1, v2), oobs2);
+}
+
+__device__ __forceinline__ void bm_set(unsigned long long (&bm)[4], int idx)
+{
+    const unsigned long long bit = 1ull << (idx & 63);
+    const int w = idx >> 6;
+    bm[0] |= (w == 0) ? bit : 0ull;
+    bm[1] |= (w == 1) ? bit : 0ull;
+    bm[2] |= (w == 2) ? bit : 0ull;
+    bm[3] |= (w == 3) ? bit : 0ull;
+}
+__device__ __forceinline__ bool bm_get(const unsigned long long (&bm)[4], int idx)
+{
+    const int w = idx >> 6;
+    const unsigned long long word = (w == 0) ? bm[0] : (w == 1) ? bm[1] : (w == 2) ? bm[2] : bm[3];
+    return (word >> (idx & 63)) & 1ull;
+}
+
+// requires mw <= 7 (W*W <= 225 bits)
+__global__ void __launch_bounds__(128)
+    k_arps_pair4(const double *__restrict__ w, int N, int mw, int f1, int f2, const short2 *__restrict__ pred,
+                 short2 *__restrict__ out, int vecSize, unsigned long long *__restrict__ ncost)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= vecSize)
+        return;
+    const int M1 = N - 3;
+    const int i = it % M1, j = it / M1;
+    const size_t fsz = (size_t)N * N;
+    const double *A1 = w + fsz * f1, *A2 = w + fsz * f2;
+    const int W = 2 * mw + 1;
+    const double oobs2 = 1.0 / 16.0;
+    double ref[16];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            ref[4 * c + r] = A1[(i + r) + (size_t)N * (j + c)];
+    unsigned long long bm[4] = {0ull, 0ull, 0ull, 0ull};
+    double costs[6];
+    int LDx[6], LDy[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+        costs[k] = 1E9;
+        LDx[k] = 0;
+        LDy[k] = 0;
+    }
+    int x = j, y = i;
+    unsigned nc = 1;
+    costs[2] = arps_cost4(ref, A2, N, i, j, oobs2);
+    bm_set(bm, mw + W * mw);
+    int maxIdx, stepSize;
+    if (j == 0)
+    {
+        stepSize = 2;
+        maxIdx = 5;
+    }
+    else
+    {
+        short2 pm = make_short2(0, 0);
+        if (pred)
+        {
+            const short2 pp = pred[it];
+            pm = make_short2((short)(pp.x - i), (short)(pp.y - j));
+        }
+        const int yTmp = abs((int)pm.x), xTmp = abs((int)pm.y);
+        stepSize = (xTmp <= yTmp) ? yTmp : xTmp;
+        if (((yTmp == 0) && (xTmp == stepSize)) || ((xTmp == 0) && (yTmp == stepSize)))
+            maxIdx = 5;
+        else
+        {
+            maxIdx = 6;
+            LDx[5] = pm.y;
+            LDy[5] = pm.x;
+        }
+    }
+    LDx[0] = 0, LDy[0] = -stepSize;
+    LDx[1] = -stepSize, LDy[1] = 0;
+    LDx[3] = stepSize, LDy[3] = 0;
+    LDx[4] = 0, LDy[4] = stepSize;
+    if (stepSize != 0)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; k++) // LDSP, arps.hpp:247-287
+        {
+            if (k == 2 || k >= maxIdx)
+                continue;
+            const int ver = y + LDy[k], hor = x + LDx[k];
+            const bool skip = (hor < 0) || (ver < 0) || (hor + 3) >= N || (ver + 3) >= N;
+            if (!skip)
+            {
+                costs[k] = arps_cost4(ref, A2, N, ver, hor, oobs2);
+                nc++;
+                const int cy = LDy[k] + mw, cx = LDx[k] + mw;
+                if (cy >= 0 && cy < W && cx >= 0 && cx < W)
+                    bm_set(bm, cy + W * cx);
+            }
+        }
+    }
+    int point = 0;
+#pragma unroll
+    for (int k = 1; k < 6; k++)
+        if (costs[k] < costs[point])
+            point = k;
+    {
+        int dx = 0, dy = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (k == point)
+            {
+                dx = LDx[k];
+                dy = LDy[k];
+            }
+        x += dx;
+        y += dy;
+    }
+    double cost = costs[0];
+#pragma unroll
+    for (int k = 1; k < 6; k++)
+        cost = (k == point) ? costs[k] : cost;
+    // SDSP, arps.hpp:299-368: offsets (hor, ver) = (0,-1), (-1,0), centre, (1,0), (0,1); ties -> lowest index
+    bool done = false;
+    unsigned nSDSP = 0;
+    do
+    {
+        double cs[5] = {1E9, 1E9, cost, 1E9, 1E9};
+        const int sdx[5] = {0, -1, 0, 1, 0}, sdy[5] = {-1, 0, 0, 0, 1};
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+        {
+            if (k == 2)
+                continue;
+            const int ver = y + sdy[k], hor = x + sdx[k];
+            bool skip = (hor < 0) || (ver < 0) || (hor + 3) >= N || (ver + 3) >= N || (hor < j - mw) || (hor > j + mw) ||
+                        (ver < i - mw) || (ver > i + mw);
+            const int bidx = (ver - i + mw) + W * (hor - j + mw);
+            if (!skip)
+                skip = bm_get(bm, bidx);
+            if (!skip)
+            {
+                cs[k] = arps_cost4(ref, A2, N, ver, hor, oobs2);
+                nc++;
+                bm_set(bm, bidx);
+            }
+        }
+        int pt = 0;
+#pragma unroll
+        for (int k = 1; k < 5; k++)
+            if (cs[k] < cs[pt])
+                pt = k;
+        // the sixth cost slot of the reference is 1e9 here and can never win against the carried centre cost
+        if (pt == 2 || nSDSP >= 1000000u)
+            done = true;
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (k == pt)
+                {
+                    x += sdx[k];
+                    y += sdy[k];
+                    cost = cs[k];
+                }
+        }
+        nSDSP++;
+    } while (!done);
+    out[it] = make_short2((short)y, (short)x);
+    if (ncost)
+        atomicAdd(ncost, (unsigned long long)nc);
+}
+
 // reference coordinates of the window's reference slice (arps.hpp:60-64)
 __global__ void k_seed_pos(short2 *__restrict__ pos, int vecSize, int M1, int ref)
 {
@@ -1186,22 +1381,34 @@ __global__ void k_c4(const unsigned *__restrict__ cnt, const int8_t *__restrict_
         c4[i] = cnt[i] ? (d2neg[i] ? dNeg : dPos) / (double)cnt[i] : 0.0;
 }
 
-// K_qform — once per frame and SVT object: q[patch][k] = u_k^T C4_patch v_k, where C4_patch is the per-voxel
-// multiplier delta2 / weights gathered along the patch trajectory (a 16 x 15 matrix).  The second-difference term of
-// the risk,  s4 = sum_voxels delta2 (U2p - 2 Uhat + U2m)  (pgure.hpp:136), is LINEAR in the reconstructed blocks
-// b = sum_k f_k(lambda) u_k v_k^T, so for every lambda it collapses to  sum_patches sum_k f_k q_k  — the perturbed
-// objects never have to be rebuilt or overlap-added during the lambda search, only thresholded.
-// 16 lanes per patch, lane g = block row g.  q: 16 doubles per patch (slot 15 unused).
-__global__ void __launch_bounds__(128)
-    k_qform(const double *__restrict__ fac, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
-            const double *__restrict__ c4, double *__restrict__ q)
+// K_qform — once per frame: q[obj][patch][k] = u_k^T C4_patch v_k for the three SVT objects, where C4_patch is the
+// per-voxel multiplier delta2 / weights gathered along the patch trajectory (a 16 x 15 matrix).  The second-difference
+// term of the risk,  s4 = sum_voxels delta2 (U2p - 2 Uhat + U2m)  (pgure.hpp:136), is LINEAR in the reconstructed
+// blocks b = sum_k f_k(lambda) u_k v_k^T, so for every lambda it collapses to  sum_patches sum_k f_k q_k  — the
+// perturbed objects never have to be rebuilt or overlap-added during the lambda search, only thresholded.
+// 16 lanes per patch (lane g = block row g), 8 patches per CTA; the U and V of the three objects (11.5 KB per patch)
+// are streamed into shared memory with cp.async while the C4 gather is in flight.
+// q: 16 doubles per patch and object (slot 15 = 0).  dynamic smem: 8 * 3 * 480 doubles.
+__global__ void __launch_bounds__(128, 2)
+    k_qform3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
+             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, const double *__restrict__ c4,
+             double *__restrict__ q0, double *__restrict__ q2, double *__restrict__ q3)
 {
+    extern __shared__ __align__(16) double sq[];
     const int g = threadIdx.x & 15;
+    double *sg = sq + (size_t)(threadIdx.x >> 4) * (3 * 480);
     int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool valid = pidx < P;
     if (!valid)
         pidx = P - 1;
-    const double *R = fac + (size_t)SVD16_REC * pidx;
+    const size_t roff = (size_t)SVD16_REC * pidx;
+    const double *R[3] = {fac0 + roff, fac2 + roff, fac3 + roff};
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+#pragma unroll
+        for (int piece = 0; piece < 15; piece++) // 480 doubles = 240 16-byte pieces per object, 15 per lane
+            cp_async16(sg + o * 480 + 2 * (piece * 16 + g), R[o] + 2 * (piece * 16 + g));
+    cp_async_commit();
     const int id = ids[pidx];
     const int r = g & 3, c = g >> 2;
     const int fsz = N * N;
@@ -1212,29 +1419,37 @@ __global__ void __launch_bounds__(128)
         const short2 p = pos[(size_t)k * vecSize + id];
         cw[k] = c4[(p.x + r) + N * (p.y + c) + fsz * k];
     }
-    double mine = 0.0;
-#pragma unroll 1
-    for (int kk = 0; kk < SVD16_N; kk++)
+    cp_async_wait<0>();
+    __syncwarp();
+    double *qd[3] = {q0, q2, q3};
+#pragma unroll
+    for (int o = 0; o < 3; o++)
     {
-        const double2 *v = reinterpret_cast<const double2 *>(R + SVD16_M * SVD16_N + SVD16_LDV * kk);
-        double z = 0.0;
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++)
+        const double *Us = sg + o * 480, *Vs = Us + SVD16_M * SVD16_N;
+        double mine = 0.0;
+#pragma unroll 1
+        for (int kk = 0; kk < SVD16_N; kk++)
         {
-            const double2 x = v[k2];
-            z = fma(cw[2 * k2], x.x, z);
-            if (2 * k2 + 1 < SVD16_N)
-                z = fma(cw[2 * k2 + 1], x.y, z);
-        }
-        double val = R[SVD16_M * kk + g] * z;
+            const double2 *v = reinterpret_cast<const double2 *>(Vs + SVD16_LDV * kk);
+            double z = 0.0;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1)
-            val += __shfl_xor_sync(0xffffffffu, val, o);
-        if (g == kk)
-            mine = val;
+            for (int k2 = 0; k2 < 8; k2++)
+            {
+                const double2 x = v[k2];
+                z = fma(cw[2 * k2], x.x, z);
+                if (2 * k2 + 1 < SVD16_N)
+                    z = fma(cw[2 * k2 + 1], x.y, z);
+            }
+            double val = Us[SVD16_M * kk + g] * z;
+#pragma unroll
+            for (int sh = 8; sh > 0; sh >>= 1)
+                val += __shfl_xor_sync(0xffffffffu, val, sh);
+            if (g == kk)
+                mine = val;
+        }
+        if (valid)
+            qd[o][(size_t)16 * pidx + g] = mine;
     }
-    if (valid)
-        q[(size_t)16 * pidx + g] = mine;
 }
 
 template <int MINB>

@@ -563,8 +563,12 @@ static int stage_window(pguresvt_handle *h, uint32_t t)
 static void arps_pair(pguresvt_handle *h, int f1, int f2, const short2 *pred, short2 *out)
 {
     const double oobs2 = 1.0 / (double)(h->p.block_size * h->p.block_size);
-    k_arps_pair<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.block_size, h->p.motion_window, f1, f2, pred, out,
-                                                          h->vecSize, oobs2, h->dNcost);
+    static const bool generic_only = getenv("PGURESVT_ARPS_GENERIC") != nullptr;
+    if (h->p.block_size == 4 && h->p.motion_window <= 7 && !generic_only)
+        k_arps_pair4<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.motion_window, f1, f2, pred, out, h->vecSize, nullptr);
+    else
+        k_arps_pair<<<cdiv(h->vecSize, 128), 128, 0, h->st>>>(h->dW, h->N, h->p.block_size, h->p.motion_window, f1, f2, pred, out,
+                                                              h->vecSize, oobs2, h->dNcost);
     LAUNCHED(h);
     h->stats[14] += 1;
 }
@@ -854,6 +858,20 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         if ((rc = stage_motion(h, t)))
             return rc;
     }
+    if (h->p.optimize_pgure)
+    {
+        StageTimer tm(h, 17);
+        if ((rc = stage_count(h, -1)))
+            return rc;
+        if (h->use_fused_eval)
+        { // per-voxel multiplier delta2/weights for the q-forms of this frame
+            const size_t wtot = h->fsz * h->win;
+            k_c4<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dC4);
+            LAUNCHED(h);
+        }
+        if ((rc = sum_u(h, &h->cur_sumU)))
+            return rc;
+    }
     {
         StageTimer tm(h, 5);
         for (int k = 0; k < h->nobj; k++)
@@ -871,25 +889,20 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
                 h->stats[h->objs[k] == 0 ? 12 : 13] = sw[1] / nwarps;
         }
     }
-    if (h->p.optimize_pgure)
-    {
+    if (h->use_fused_eval)
+    { // bilinear forms q = u^T C4 v of every singular triplet of the three objects (see k_qform3)
         StageTimer tm(h, 17);
-        if ((rc = stage_count(h, -1)))
-            return rc;
-        if (h->use_fused_eval)
-        { // per-voxel multiplier delta2/weights, then the bilinear forms q = u^T C4 v of every triplet (see k_qform)
-            const size_t wtot = h->fsz * h->win;
-            k_c4<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dC4);
-            LAUNCHED(h);
-            const int objs3[3] = {0, 2, 3};
-            for (int k = 0; k < 3; k++)
-            {
-                k_qform<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[objs3[k]], h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dC4, h->dQ[k]);
-                LAUNCHED(h);
-            }
+        static bool attr_set = false;
+        const int smem = 8 * 3 * 480 * (int)sizeof(double);
+        if (!attr_set)
+        {
+            CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
         }
-        if ((rc = sum_u(h, &h->cur_sumU)))
-            return rc;
+        k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
+                                                       h->dC4, h->dQ[0], h->dQ[1], h->dQ[2]);
+        LAUNCHED(h);
+        CU(cudaGetLastError());
     }
     h->cur_t = t;
     return PGS_OK;
