@@ -121,8 +121,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--frames-per-step", type=int, default=4)
-    ap.add_argument("--noise", default="auto", choices=["auto", "known", "estimate"])
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--noise", default="estimate", choices=["known", "estimate"],
+                    help="estimate: alpha/mu/sigma unknown, estimated per frame on the GPU (the reference's default usage); "
+                         "known: alpha/mu/sigma supplied (isolates SVD + lambda search)")
     ap.add_argument("--fixed-lambda", action="store_true", help="configs[2]-style pure SVT path (no PGURE search)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -816,11 +816,6 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
                                  double &alpha, double &mu, double &sigma, long long *launches, std::string &err,
                                  long long frame0 = -1, double umax = 0.0)
 {
-    if (method != 4 && !(method < 1 || method > 4))
-    {
-        err = "noise_method 1-3 (mode-based estimates, noise.hpp:115-137) are not implemented on the GPU path; use noise_method=4";
-        return 3;
-    }
     if (N < 16 || (N & (N - 1)) != 0 || N > 4096)
     {
         err = "quadtree noise estimation requires square frames with a power-of-two side between 16 and 4096";
@@ -913,8 +908,71 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
     ws.fit_iters = fit[2];
-    // noise.hpp:113,139-146 (method 4; the default branch is the same)
-    alpha = (alpha >= 0.) ? alpha : fit[0];
+    alpha = (alpha >= 0.) ? alpha : fit[0]; // noise.hpp:113
+    if (method >= 1 && method <= 3)
+    {
+        // noise.hpp:115-137: mode-based variants.  They work on the samples sorted by mean (stable) — scalar
+        // post-processing of the GPU-computed samples, done on the host.
+        std::vector<size_t> idx(n);
+        for (size_t k = 0; k < n; k++)
+            idx[k] = k;
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return xs[a] < xs[b]; });
+        std::vector<double> rm(n), rv(n);
+        for (size_t k = 0; k < n; k++)
+        {
+            rm[k] = xs[idx[k]];
+            rv[k] = ys[idx[k]];
+        }
+        auto compute_mode = [](const std::vector<double> &A) { // ComputeMode, noise.hpp:273-301 (first maximal count wins)
+            const size_t nn = A.size();
+            const double M = *std::max_element(A.begin(), A.end()), dyn = 1. * nn;
+            std::vector<double> a(nn);
+            for (size_t i = 0; i < nn; i++)
+                a[i] = std::round(A[i] * dyn / M);
+            std::unordered_map<double, std::pair<unsigned, size_t>> cnt; // value -> (count, first index)
+            for (size_t i = 0; i < nn; i++)
+            {
+                auto it = cnt.find(a[i]);
+                if (it == cnt.end())
+                    cnt.emplace(a[i], std::make_pair(1u, i));
+                else
+                    it->second.first++;
+            }
+            unsigned best = 0;
+            size_t first = 0;
+            double val = 0.;
+            for (auto &kv : cnt)
+                if (kv.second.first > best || (kv.second.first == best && kv.second.second < first))
+                {
+                    best = kv.second.first;
+                    first = kv.second.second;
+                    val = kv.first;
+                }
+            return val * (M / dyn);
+        };
+        auto head = [](const std::vector<double> &a, size_t last) { return std::vector<double>(a.begin(), a.begin() + last + 1); };
+        if (method == 1)
+        {
+            const int L = (int)std::floor(1. * ((unsigned)(N * N) / (unsigned)n));
+            const size_t last = (size_t)std::round(0.05 * L);
+            mu = (mu >= 0.) ? mu : compute_mode(head(rm, last));
+            const double dSi = compute_mode(head(rv, last));
+            sigma = (sigma >= 0.) ? sigma : std::sqrt(dSi);
+        }
+        else if (method == 2)
+        {
+            mu = (mu >= 0.) ? mu : compute_mode(rm);
+            const double dSi = compute_mode(rv);
+            sigma = (sigma >= 0.) ? sigma : std::sqrt(std::max(dSi, std::max(fit[1] + fit[0] * dSi, 0.)));
+        }
+        else
+        {
+            mu = (mu >= 0.) ? mu : compute_mode(rm);
+            sigma = (sigma >= 0.) ? sigma : std::sqrt(std::fabs(fit[1] + fit[0] * mu));
+        }
+        return 0;
+    }
+    // noise.hpp:139-146 (method 4; the default branch is the same)
     mu = (mu >= 0.) ? mu : fit[3];
     sigma = (sigma >= 0.) ? sigma : std::sqrt(std::fabs(fit[1] + fit[0] * mu));
     return 0;

@@ -383,6 +383,19 @@ def test_noise_estimate_vs_oracle(N):
     h.close()
 
 
+@pytest.mark.parametrize("method", [1, 2, 3])
+def test_noise_methods_1_to_3(method):
+    """The mode-based variants of noise.hpp:115-137 (non-default, 'currently undocumented' in the reference)."""
+    X, _ = synthetic_sequence(64, 15, seed=64)
+    h = bridge.Handle(X, optimize_pgure=True, random_seed=1, noise_method=method)
+    got = h.probe_noise(7)
+    u = X.astype(np.float64)
+    u /= u.max()
+    want = orc.noise_estimate(u, method)[:3]
+    assert np.allclose(got, want, rtol=1e-6, atol=0), (got, want)
+    h.close()
+
+
 def test_default_api_estimates_noise(golden):
     """SVT() with the reference's defaults: noise parameters unknown -> estimated per frame on the GPU."""
     X = golden["X"]
