@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <string>
 #include <unordered_map>
@@ -586,6 +587,7 @@ struct NoiseWorkspace
     int grid = 0;
     long long n_split_calls = 0, n_regions = 0, n_samples = 0, n_big = 0, slices_analysed = 0, slices_reused = 0;
     double fit_iters = 0;
+    double t_split = 0, t_replay = 0, t_leaf = 0, t_fit = 0; // host wall-clock seconds per phase (diagnostics)
     std::unordered_map<long long, NoiseSliceSamples> cache;
     void release()
     {
@@ -672,9 +674,12 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
         if (launches)
             (*launches)++;
     }
+    const auto tp0 = std::chrono::steady_clock::now();
     std::vector<unsigned char> fl(nflags);
     NCU(cudaMemcpyAsync(fl.data(), ws.dFlags, nflags, cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
+    const auto tp1 = std::chrono::steady_clock::now();
+    ws.t_split += std::chrono::duration<double>(tp1 - tp0).count();
 
     // replay QuadTree() (noise.hpp:419-458) against the decision table
     struct Node
@@ -741,6 +746,8 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
         }
         sample_region.push_back(ridx);
     }
+    const auto tp2 = std::chrono::steady_clock::now();
+    ws.t_replay += std::chrono::duration<double>(tp2 - tp1).count();
     const size_t nreg = regions.size(), nbig = big.size();
     ws.n_regions += (long long)nreg;
     ws.n_samples += (long long)sample_region.size();
@@ -795,6 +802,7 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
     NCU(cudaMemcpyAsync(leaf.data(), ws.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
+    ws.t_leaf += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp2).count();
     outS.xs.clear();
     outS.ys.clear();
     outS.xs.reserve(sample_region.size());
@@ -904,10 +912,16 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
             (*launches)++;
     }
     double fit[4];
+    const auto tf0 = std::chrono::steady_clock::now();
     NCU(cudaMemcpyAsync(fit, ws.dFit, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
+    ws.t_fit += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
     ws.fit_iters = fit[2];
+    if (getenv("PGURESVT_NOISE_TIMING"))
+        fprintf(stderr, "[noise] split+sync %.2f ms, replay %.2f ms, leaf+big %.2f ms, fit %.2f ms (%g iters), slices analysed %lld reused %lld, regions %lld samples %lld\n",
+                ws.t_split * 1e3, ws.t_replay * 1e3, ws.t_leaf * 1e3, ws.t_fit * 1e3, ws.fit_iters, ws.slices_analysed, ws.slices_reused,
+                ws.n_regions, ws.n_samples);
     alpha = (alpha >= 0.) ? alpha : fit[0]; // noise.hpp:113
     if (method >= 1 && method <= 3)
     {

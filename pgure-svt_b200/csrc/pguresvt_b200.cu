@@ -101,7 +101,7 @@ struct pguresvt_handle
 
     std::vector<double> xmax, zmax; // per resident frame
     std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
-    bool uploaded = false, prefiltered = false, perturbed = false;
+    bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false;
     long long cur_t = -1;
     bool cur_opt_ready = false;
     double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
@@ -673,12 +673,11 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
                                                                   nullptr, max_sweeps, tol2, big2, h->dSweeps);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
         {
-            static bool attr_set = false;
             const int smem_warm = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
-            if (!attr_set)
-            {
+            if (!h->attr_warm)
+            { // per device: the handle is bound to one device
                 CU(cudaFuncSetAttribute(k_svd16_l4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
-                attr_set = true;
+                h->attr_warm = true;
             }
             k_svd16_l4<1><<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
                                                                   h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
@@ -892,12 +891,11 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     if (h->use_fused_eval)
     { // bilinear forms q = u^T C4 v of every singular triplet of the three objects (see k_qform3)
         StageTimer tm(h, 17);
-        static bool attr_set = false;
         const int smem = 8 * 3 * 480 * (int)sizeof(double);
-        if (!attr_set)
+        if (!h->attr_qform)
         {
             CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
+            h->attr_qform = true;
         }
         k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
                                                        h->dC4, h->dQ[0], h->dQ[1], h->dQ[2]);
