@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -280,7 +281,6 @@ struct GridScratch
 {
     double *partials; // [4][8][grid]
     unsigned *ghist;  // [4][256], zero at launch
-    int *counters;    // unused by the device; host zeroes ghist before every launch
 };
 
 template <int NT, int NQ>
@@ -576,18 +576,44 @@ struct NoiseSliceSamples
     std::vector<double> xs, ys; // robust means / variances in the reference's node order (duplicates included)
 };
 
-struct NoiseWorkspace
+// device scratch of one in-flight slice analysis (own stream, so several slices overlap on the GPU while their
+// host-side quadtree walks run on separate host threads)
+struct NoiseSliceCtx
 {
+    cudaStream_t st = nullptr;
     unsigned char *dFlags = nullptr;
     NoiseRegion *dRegions = nullptr;
     int *dBig = nullptr;
-    double *dScratch = nullptr, *dLeaf = nullptr, *dFit = nullptr, *dPartials = nullptr, *dX = nullptr, *dY = nullptr;
+    double *dScratch = nullptr, *dLeaf = nullptr, *dPartials = nullptr;
     unsigned *dHist = nullptr;
-    size_t capFlags = 0, capRegions = 0, capScratch = 0, capSamples = 0, capBig = 0;
-    int grid = 0;
-    long long n_split_calls = 0, n_regions = 0, n_samples = 0, n_big = 0, slices_analysed = 0, slices_reused = 0;
-    double fit_iters = 0;
-    double t_split = 0, t_replay = 0, t_leaf = 0, t_fit = 0; // host wall-clock seconds per phase (diagnostics)
+    size_t capFlags = 0, capRegions = 0, capScratch = 0, capBig = 0;
+    long long n_regions = 0, n_samples = 0, n_big = 0, launches = 0;
+    double t_split = 0, t_replay = 0, t_leaf = 0;
+    std::string err;
+    void release()
+    {
+        auto F = [](void *p) {
+            if (p)
+                cudaFree(p);
+        };
+        F(dFlags), F(dRegions), F(dBig), F(dScratch), F(dLeaf), F(dPartials), F(dHist);
+        if (st)
+            cudaStreamDestroy(st);
+        *this = NoiseSliceCtx();
+    }
+};
+
+#define NOISE_MAX_CTX 16
+
+struct NoiseWorkspace
+{
+    NoiseSliceCtx ctx[NOISE_MAX_CTX];
+    double *dFit = nullptr, *dPartials = nullptr, *dX = nullptr, *dY = nullptr;
+    unsigned *dHist = nullptr;
+    size_t capSamples = 0;
+    int grid = 0, device = 0;
+    long long slices_analysed = 0, slices_reused = 0;
+    double fit_iters = 0, t_fit = 0, t_slices = 0;
     std::unordered_map<long long, NoiseSliceSamples> cache;
     void release()
     {
@@ -595,9 +621,11 @@ struct NoiseWorkspace
             if (p)
                 cudaFree(p);
         };
-        F(dFlags), F(dRegions), F(dBig), F(dScratch), F(dLeaf), F(dFit), F(dPartials), F(dHist), F(dX), F(dY);
-        dFlags = nullptr, dRegions = nullptr, dBig = nullptr, dScratch = dLeaf = dFit = dPartials = dX = dY = nullptr, dHist = nullptr;
-        capFlags = capRegions = capScratch = capSamples = capBig = 0;
+        for (auto &c : ctx)
+            c.release();
+        F(dFit), F(dPartials), F(dHist), F(dX), F(dY);
+        dFit = dPartials = dX = dY = nullptr, dHist = nullptr;
+        capSamples = 0;
         cache.clear();
     }
 };
@@ -632,16 +660,26 @@ static int noise_init(NoiseWorkspace &ws, int sm_count, std::string &err)
     if (ws.dFit)
         return 0;
     ws.grid = sm_count > 0 ? sm_count : 148;
+    NCU(cudaGetDevice(&ws.device));
     NCU(cudaMalloc(&ws.dFit, 8 * sizeof(double)));
     NCU(cudaMalloc(&ws.dPartials, (size_t)4 * 8 * ws.grid * sizeof(double)));
     NCU(cudaMalloc(&ws.dHist, 4 * 256 * sizeof(unsigned)));
     return 0;
 }
 
-// quadtree + leaf statistics of ONE slice (N x N doubles at dA) -> samples in the reference's order
-static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cudaStream_t st, NoiseSliceSamples &outS,
-                               long long *launches, std::string &err)
+// quadtree + leaf statistics of ONE slice (N x N doubles at dA) -> samples in the reference's order.
+// big_grid: CTAs of the cooperative kernel for the large regions (fewer when several slices are in flight).
+static int noise_analyse_slice(NoiseSliceCtx &cx, const double *dA, int N, int big_grid, int full_grid, NoiseSliceSamples &outS)
 {
+    std::string &err = cx.err;
+    cudaStream_t st = cx.st;
+    if (!st)
+    {
+        NCU(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+        st = cx.st;
+        NCU(cudaMalloc(&cx.dPartials, (size_t)4 * 8 * full_grid * sizeof(double)));
+        NCU(cudaMalloc(&cx.dHist, 4 * 256 * sizeof(unsigned)));
+    }
     // level table: sides N, N/2, ..., 8 (side 8 never splits but is needed to address regions)
     std::vector<int> sides, offs;
     int per_slice = 0, per_slice_flags = 0;
@@ -654,13 +692,14 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
             per_slice_flags = per_slice;
     }
     const size_t nflags = (size_t)per_slice_flags;
-    if (ws.capFlags < nflags)
+    if (cx.capFlags < nflags)
     {
-        if (ws.dFlags)
-            cudaFree(ws.dFlags);
-        NCU(cudaMalloc(&ws.dFlags, nflags));
-        ws.capFlags = nflags;
+        if (cx.dFlags)
+            cudaFree(cx.dFlags);
+        NCU(cudaMalloc(&cx.dFlags, nflags));
+        cx.capFlags = nflags;
     }
+    const auto tp0 = std::chrono::steady_clock::now();
     for (size_t l = 0; l < sides.size(); l++)
     {
         const int s = sides[l], nb = (N / s) * (N / s);
@@ -668,18 +707,16 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
             break;
         const double ft = noise_ftest0025(s);
         if (s >= 128)
-            k_noise_split<1024><<<dim3(nb, 1), 1024, 0, st>>>(dA, N, s, ft, ws.dFlags, per_slice_flags, offs[l]);
+            k_noise_split<1024><<<dim3(nb, 1), 1024, 0, st>>>(dA, N, s, ft, cx.dFlags, per_slice_flags, offs[l]);
         else
-            k_noise_split<128><<<dim3(nb, 1), 128, 0, st>>>(dA, N, s, ft, ws.dFlags, per_slice_flags, offs[l]);
-        if (launches)
-            (*launches)++;
+            k_noise_split<128><<<dim3(nb, 1), 128, 0, st>>>(dA, N, s, ft, cx.dFlags, per_slice_flags, offs[l]);
+        cx.launches++;
     }
-    const auto tp0 = std::chrono::steady_clock::now();
     std::vector<unsigned char> fl(nflags);
-    NCU(cudaMemcpyAsync(fl.data(), ws.dFlags, nflags, cudaMemcpyDeviceToHost, st));
+    NCU(cudaMemcpyAsync(fl.data(), cx.dFlags, nflags, cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     const auto tp1 = std::chrono::steady_clock::now();
-    ws.t_split += std::chrono::duration<double>(tp1 - tp0).count();
+    cx.t_split += std::chrono::duration<double>(tp1 - tp0).count();
 
     // replay QuadTree() (noise.hpp:419-458) against the decision table
     struct Node
@@ -698,7 +735,6 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
     tree.push_back({0, 0, N, 0});
     auto enter = [&](int part) {
         const Node nd = tree[part];
-        ws.n_split_calls++;
         if (nd.s <= 8)
             return;
         if (!fl[offs[nd.lvl] + (nd.i / nd.s) + (N / nd.s) * (nd.j / nd.s)])
@@ -747,62 +783,59 @@ static int noise_analyse_slice(NoiseWorkspace &ws, const double *dA, int N, cuda
         sample_region.push_back(ridx);
     }
     const auto tp2 = std::chrono::steady_clock::now();
-    ws.t_replay += std::chrono::duration<double>(tp2 - tp1).count();
+    cx.t_replay += std::chrono::duration<double>(tp2 - tp1).count();
     const size_t nreg = regions.size(), nbig = big.size();
-    ws.n_regions += (long long)nreg;
-    ws.n_samples += (long long)sample_region.size();
-    ws.n_big += (long long)nbig;
-    if (ws.capRegions < nreg)
+    cx.n_regions += (long long)nreg;
+    cx.n_samples += (long long)sample_region.size();
+    cx.n_big += (long long)nbig;
+    if (cx.capRegions < nreg)
     {
-        if (ws.dRegions)
-            cudaFree(ws.dRegions);
-        if (ws.dLeaf)
-            cudaFree(ws.dLeaf);
-        NCU(cudaMalloc(&ws.dRegions, nreg * sizeof(NoiseRegion)));
-        NCU(cudaMalloc(&ws.dLeaf, nreg * 2 * sizeof(double)));
-        ws.capRegions = nreg;
+        if (cx.dRegions)
+            cudaFree(cx.dRegions);
+        if (cx.dLeaf)
+            cudaFree(cx.dLeaf);
+        NCU(cudaMalloc(&cx.dRegions, nreg * sizeof(NoiseRegion)));
+        NCU(cudaMalloc(&cx.dLeaf, nreg * 2 * sizeof(double)));
+        cx.capRegions = nreg;
     }
-    if (ws.capScratch < (size_t)scratch_need)
+    if (cx.capScratch < (size_t)scratch_need)
     {
-        if (ws.dScratch)
-            cudaFree(ws.dScratch);
-        NCU(cudaMalloc(&ws.dScratch, (size_t)scratch_need * sizeof(double)));
-        ws.capScratch = (size_t)scratch_need;
+        if (cx.dScratch)
+            cudaFree(cx.dScratch);
+        NCU(cudaMalloc(&cx.dScratch, (size_t)scratch_need * sizeof(double)));
+        cx.capScratch = (size_t)scratch_need;
     }
-    if (ws.capBig < nbig)
+    if (cx.capBig < nbig)
     {
-        if (ws.dBig)
-            cudaFree(ws.dBig);
-        NCU(cudaMalloc(&ws.dBig, nbig * sizeof(int)));
-        ws.capBig = nbig;
+        if (cx.dBig)
+            cudaFree(cx.dBig);
+        NCU(cudaMalloc(&cx.dBig, nbig * sizeof(int)));
+        cx.capBig = nbig;
     }
-    NCU(cudaMemcpyAsync(ws.dRegions, regions.data(), nreg * sizeof(NoiseRegion), cudaMemcpyHostToDevice, st));
-    NCU(cudaMemcpyAsync(ws.dBig, big.data(), nbig * sizeof(int), cudaMemcpyHostToDevice, st));
+    NCU(cudaMemcpyAsync(cx.dRegions, regions.data(), nreg * sizeof(NoiseRegion), cudaMemcpyHostToDevice, st));
+    NCU(cudaMemcpyAsync(cx.dBig, big.data(), nbig * sizeof(int), cudaMemcpyHostToDevice, st));
     // small regions: one CTA each (large ones return immediately inside the kernel)
-    k_noise_leaf<128><<<(unsigned)nreg, 128, 0, st>>>(dA, N, ws.dRegions, ws.dScratch, ws.dLeaf, NOISE_BIG_SIDE);
-    if (launches)
-        (*launches)++;
+    k_noise_leaf<128><<<(unsigned)nreg, 128, 0, st>>>(dA, N, cx.dRegions, cx.dScratch, cx.dLeaf, NOISE_BIG_SIDE);
+    cx.launches++;
     {
         GridScratch gs;
-        gs.partials = ws.dPartials;
-        gs.ghist = ws.dHist;
-        gs.counters = nullptr;
-        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 256 * sizeof(unsigned), st));
+        gs.partials = cx.dPartials;
+        gs.ghist = cx.dHist;
+        NCU(cudaMemsetAsync(cx.dHist, 0, 4 * 256 * sizeof(unsigned), st));
         const double *a0 = dA;
         int a1 = N, a4 = (int)nbig;
-        const NoiseRegion *a2 = ws.dRegions;
-        const int *a3 = ws.dBig;
-        double *a5 = ws.dScratch, *a6 = ws.dLeaf;
+        const NoiseRegion *a2 = cx.dRegions;
+        const int *a3 = cx.dBig;
+        double *a5 = cx.dScratch, *a6 = cx.dLeaf;
         void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
-        NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(ws.grid), dim3(512), args, 0, st));
-        if (launches)
-            (*launches)++;
+        NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(big_grid), dim3(512), args, 0, st));
+        cx.launches++;
     }
     std::vector<double> leaf(nreg * 2);
-    NCU(cudaMemcpyAsync(leaf.data(), ws.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCU(cudaMemcpyAsync(leaf.data(), cx.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
-    ws.t_leaf += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp2).count();
+    cx.t_leaf += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp2).count();
     outS.xs.clear();
     outS.ys.clear();
     outS.xs.reserve(sample_region.size());
@@ -832,39 +865,78 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
     int rc = noise_init(ws, sm_count, err);
     if (rc)
         return rc;
-    std::vector<const NoiseSliceSamples *> parts(T);
-    std::vector<NoiseSliceSamples> local;
-    local.reserve(T);
+    std::vector<NoiseSliceSamples *> parts(T);
+    std::vector<NoiseSliceSamples> local(frame0 >= 0 ? 0 : T);
     if (frame0 >= 0)
     { // drop cache entries that can no longer be part of a window
         for (auto it = ws.cache.begin(); it != ws.cache.end();)
             it = (it->first < frame0 - T || it->first > frame0 + 2 * T) ? ws.cache.erase(it) : std::next(it);
     }
+    std::vector<int> todo;
     for (int k = 0; k < T; k++)
     {
-        const double *dA = dU + (size_t)N * N * k;
         if (frame0 >= 0)
         {
-            NoiseSliceSamples &e = ws.cache[frame0 + k];
+            NoiseSliceSamples &e = ws.cache[frame0 + k]; // references into unordered_map stay valid across inserts
+            parts[k] = &e;
             if (e.umax != umax || e.xs.empty())
             {
                 e.umax = umax;
-                if ((rc = noise_analyse_slice(ws, dA, N, st, e, launches, err)))
-                    return rc;
-                ws.slices_analysed++;
+                todo.push_back(k);
             }
             else
                 ws.slices_reused++;
-            parts[k] = &e;
         }
         else
         {
-            local.emplace_back();
-            if ((rc = noise_analyse_slice(ws, dA, N, st, local.back(), launches, err)))
-                return rc;
-            ws.slices_analysed++;
-            parts[k] = &local.back();
+            parts[k] = &local[k];
+            todo.push_back(k);
         }
+    }
+    if (!todo.empty())
+    {
+        // the window cube was produced on `st`: make it visible to the per-slice streams
+        NCU(cudaStreamSynchronize(st));
+        const auto ts0 = std::chrono::steady_clock::now();
+        const int nthreads = (int)std::min<size_t>(todo.size(), NOISE_MAX_CTX);
+        const int big_grid = std::max(8, ws.grid / nthreads);
+        std::vector<int> rcs(nthreads, 0);
+        auto worker = [&](int w) {
+            cudaSetDevice(ws.device);
+            for (size_t q = (size_t)w; q < todo.size(); q += (size_t)nthreads)
+            {
+                const int k = todo[q];
+                const int r = noise_analyse_slice(ws.ctx[w], dU + (size_t)N * N * k, N, big_grid, ws.grid, *parts[k]);
+                if (r)
+                {
+                    rcs[w] = r;
+                    return;
+                }
+            }
+        };
+        if (nthreads == 1)
+            worker(0);
+        else
+        {
+            std::vector<std::thread> th;
+            for (int w = 0; w < nthreads; w++)
+                th.emplace_back(worker, w);
+            for (auto &t : th)
+                t.join();
+        }
+        for (int w = 0; w < nthreads; w++)
+        {
+            if (launches)
+                *launches += ws.ctx[w].launches;
+            ws.ctx[w].launches = 0;
+            if (rcs[w])
+            {
+                err = ws.ctx[w].err;
+                return rcs[w];
+            }
+        }
+        ws.slices_analysed += (long long)todo.size();
+        ws.t_slices += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
     }
     size_t n = 0, ny = 0;
     for (int k = 0; k < T; k++)
@@ -901,7 +973,6 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
         GridScratch gs;
         gs.partials = ws.dPartials;
         gs.ghist = ws.dHist;
-        gs.counters = nullptr;
         NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 256 * sizeof(unsigned), st));
         const double *a0 = ws.dX, *a1 = ws.dY;
         int a2 = (int)n;
@@ -919,9 +990,8 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
     ws.t_fit += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
     ws.fit_iters = fit[2];
     if (getenv("PGURESVT_NOISE_TIMING"))
-        fprintf(stderr, "[noise] split+sync %.2f ms, replay %.2f ms, leaf+big %.2f ms, fit %.2f ms (%g iters), slices analysed %lld reused %lld, regions %lld samples %lld\n",
-                ws.t_split * 1e3, ws.t_replay * 1e3, ws.t_leaf * 1e3, ws.t_fit * 1e3, ws.fit_iters, ws.slices_analysed, ws.slices_reused,
-                ws.n_regions, ws.n_samples);
+        fprintf(stderr, "[noise] slices %.2f ms (analysed %lld, reused %lld), fit %.2f ms (%g iters), %zu samples\n", ws.t_slices * 1e3,
+                ws.slices_analysed, ws.slices_reused, ws.t_fit * 1e3, ws.fit_iters, n);
     alpha = (alpha >= 0.) ? alpha : fit[0]; // noise.hpp:113
     if (method >= 1 && method <= 3)
     {

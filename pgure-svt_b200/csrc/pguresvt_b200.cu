@@ -103,7 +103,6 @@ struct pguresvt_handle
     std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
     bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false;
     long long cur_t = -1;
-    bool cur_opt_ready = false;
     double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
     double stats[PGS_NSTATS] = {0};
@@ -359,7 +358,6 @@ static int invalidate(pguresvt_handle *h)
         tg.frame = -1;
     h->prefiltered = false;
     h->cur_t = -1;
-    h->cur_opt_ready = false;
     return PGS_OK;
 }
 
