@@ -468,3 +468,47 @@ def test_cli_config1_example_tif(tmp_path):
     # truncation makes +-1 count differences possible where the double result sits within 1e-6 of an integer
     diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-4
+
+
+# ------------------------------------------------------------------ edge cases of the driver logic
+@pytest.mark.parametrize("kw,N,F", [
+    (dict(trajectory_length=15), 32, 15),                      # sequence exactly one window long: every frame shares it
+    (dict(trajectory_length=3), 32, 5),                        # 16x3 Casorati matrices (generic SVD kernel)
+    (dict(trajectory_length=1), 32, 3),                        # no temporal dimension at all
+    (dict(trajectory_length=15, patch_size=3), 30, 12),        # bs^2 < T -> Nt = 8, 9-slice windows
+    (dict(trajectory_length=7, patch_size=5, patch_overlap=3), 40, 9),   # skewed patch set with uncovered pixels (Q5, Q17)
+    (dict(trajectory_length=15, motion_window=3, motion_filter=1), 48, 16),  # small search window, 3x3 median, non-2^N frame
+    (dict(trajectory_length=9, patch_size=8, patch_overlap=4), 64, 11),   # 64x9 Casorati matrices
+])
+def test_edge_case_configurations_fixed_lambda(kw, N, F):
+    X, _ = synthetic_sequence(N, F, seed=N + F)
+    # noise parameters given so that the reference's 2^N check (svt.py:262-271) does not apply to odd frame sizes
+    args = dict(optimize_pgure=False, lambda1=0.2, random_seed=1, noise_alpha=0.1, noise_mu=0.1, noise_sigma=0.1)
+    args.update(kw)
+    s = SVT(**args).denoise(X)
+    ref, _ = orc.pguresvt(X, **args)
+    assert np.isfinite(s.Y_).all()
+    assert per_frame_rel_err(s.Y_, ref) < PIX_TOL
+
+
+def test_edge_case_pgure_small_windows():
+    """PGURE search on a configuration that takes the generic kernels (patch 5, trajectory 7)."""
+    X, _ = synthetic_sequence(40, 9, seed=77)
+    args = dict(trajectory_length=7, patch_size=5, patch_overlap=2, optimize_pgure=True, lambda1=-1.0, noise_alpha=0.05,
+                noise_mu=0.03, noise_sigma=0.03, random_seed=3)
+    s = SVT(**{k: v for k, v in args.items() if k != "lambda1"}).denoise(X)
+    ref, est = orc.pguresvt(X, **args)
+    rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
+    assert rel.max() < LAM_TOL, rel
+    assert per_frame_rel_err(s.Y_, ref) < 1e-4
+
+
+def test_too_short_sequence_and_bad_arguments_are_errors_not_crashes():
+    X, _ = synthetic_sequence(32, 10, seed=1)
+    with pytest.raises(RuntimeError, match="fewer than"):
+        SVT(optimize_pgure=False, lambda1=0.1).denoise(X)          # 10 frames < 15-frame window
+    with pytest.raises(RuntimeError, match="square"):
+        bridge.pguresvt_u16(np.zeros((32, 48, 16), dtype=np.uint16, order="F"), optimize_pgure=False, lambda1=0.1)
+    with pytest.raises(RuntimeError, match="initial step|cannot start"):
+        bridge.pguresvt_u16(np.zeros((32, 32, 16), dtype=np.uint16, order="F") + 5, optimize_pgure=True, lambda1=0.0,
+                            noise_alpha=0.1, noise_mu=0.1, noise_sigma=0.1)  # the CLI's lambda = 0.0 start (SURVEY Q13)
