@@ -1591,36 +1591,43 @@ __global__ void __launch_bounds__(128, MINB)
 }
 
 // voxel pass of the fused evaluation: Uhat = acc0 / weights (non-finite -> 0, svt.hpp:163-164);
-// s1 = sum (Uhat - U)^2, s5 = sum Uhat.  partial: gridDim.x * 2 doubles
-__global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, const double *__restrict__ acc0,
-                            size_t tot, double *__restrict__ partial)
+// s1 = sum (Uhat - U)^2, s5 = sum Uhat; the accumulator is cleared on the way for the next evaluation, and the
+// per-CTA s4 partials of k_eval3 are folded in (third sum) so that one fixed-order reduction finishes all three.
+// partial: gridDim.x * 3 doubles
+__global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
+                            const double *__restrict__ s4part, int ns4, double *__restrict__ partial)
 {
-    double s1 = 0, s5 = 0;
+    double s1 = 0, s5 = 0, s4 = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
         const double v0 = norm_or_zero(acc0[i], cnt[i]);
+        acc0[i] = 0.0;
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
         s5 += v0;
     }
-    __shared__ double sm[2][32];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns4; i += gridDim.x * blockDim.x)
+        s4 += s4part[i];
+    __shared__ double sm[3][32];
     s1 = warp_sum(s1);
     s5 = warp_sum(s5);
+    s4 = warp_sum(s4);
     if ((threadIdx.x & 31) == 0)
     {
         sm[0][threadIdx.x >> 5] = s1;
         sm[1][threadIdx.x >> 5] = s5;
+        sm[2][threadIdx.x >> 5] = s4;
     }
     __syncthreads();
     if (threadIdx.x < 32)
     {
 #pragma unroll
-        for (int q = 0; q < 2; q++)
+        for (int q = 0; q < 3; q++)
         {
             double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
             r = warp_sum(r);
             if (threadIdx.x == 0)
-                partial[(size_t)blockIdx.x * 2 + q] = r;
+                partial[(size_t)blockIdx.x * 3 + q] = r;
         }
     }
 }

@@ -26,6 +26,21 @@ __global__ void k_atomic(double *acc, size_t n, int reps, int stride)
         atomicAdd(acc + j, 1.0);
     }
 }
+// integer (fixed-point) and FP32 variants of the RED pattern the overlap-add uses: 16 lanes cover 4 columns x 4 rows
+template <typename T>
+__global__ void k_atomic_patch(T *acc, int N, int reps)
+{
+    const int g = threadIdx.x & 15;
+    const size_t patch = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int M1 = N - 3;
+    const int y = (int)(patch % M1), x = (int)((patch / M1) % M1);
+    for (int k = 0; k < reps; k++)
+    {
+        const int yy = min(max(y + ((int)(patch * 7 + k) % 5) - 2, 0), M1 - 1);
+        const size_t vox = (size_t)(yy + (g & 3)) + (size_t)N * (x + (g >> 2)) + (size_t)N * N * k;
+        atomicAdd(acc + vox, (T)1);
+    }
+}
 __global__ void k_copy(const double4 *a, double4 *b, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -84,6 +99,27 @@ int main()
         float ms = timeit(e0, e1);
         atom_g[mode] = threads * 16.0 / (ms * 1e-3) / 1e9;
     }
+    // patch-pattern REDs: double vs unsigned long long vs float (1024^2 x 15 cube, 1.04M patches x 15 slices x 16 lanes)
+    double patch_g[3];
+    {
+        const int N = 1024;
+        const size_t np = (size_t)(N - 3) * (N - 3);
+        const unsigned blocks = (unsigned)((np * 16 + 127) / 128);
+        for (int v = 0; v < 3; v++)
+        {
+            cudaMemset(acc, 0, n * sizeof(double));
+            for (int rep = 0; rep < 2; rep++)
+            {
+                cudaEventRecord(e0);
+                if (v == 0) k_atomic_patch<double><<<blocks, 128>>>(acc, N, 15);
+                if (v == 1) k_atomic_patch<unsigned long long><<<blocks, 128>>>((unsigned long long *)acc, N, 15);
+                if (v == 2) k_atomic_patch<float><<<blocks, 128>>>((float *)acc, N, 15);
+                cudaEventRecord(e1);
+            }
+            float ms = timeit(e0, e1);
+            patch_g[v] = np * 16.0 * 15 / (ms * 1e-3) / 1e9;
+        }
+    }
     // copy
     size_t cn = (size_t)1 << 27; // 128M double4 = 4 GB
     double4 *a, *b;
@@ -101,7 +137,8 @@ int main()
         if (gbs > copy) copy = gbs;
     }
     printf("{\"dfma_tflops\": %.2f, \"dfma_tflops_sustained\": %.2f, \"atomic_f64_gops_coalesced\": %.1f, "
-           "\"atomic_f64_gops_strided\": %.1f, \"copy_gbs\": %.1f, \"cuda_error\": \"%s\"}\n",
-           best, sustained, atom_g[0], atom_g[1], copy, cudaGetErrorString(cudaGetLastError()));
+           "\"atomic_f64_gops_strided\": %.1f, \"patch_red_f64_gops\": %.1f, \"patch_red_u64_gops\": %.1f, \"patch_red_f32_gops\": %.1f, "
+           "\"copy_gbs\": %.1f, \"cuda_error\": \"%s\"}\n",
+           best, sustained, atom_g[0], atom_g[1], patch_g[0], patch_g[1], patch_g[2], copy, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -101,7 +101,7 @@ struct pguresvt_handle
 
     std::vector<double> xmax, zmax; // per resident frame
     std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
-    bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false;
+    bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false, acc0_clean = false;
     long long cur_t = -1;
     double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
@@ -725,6 +725,8 @@ static int stage_count(pguresvt_handle *h, int only_k)
 
 static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) // SVT::Reconstruct, svt.hpp:121-160
 {
+    if (obj == 0)
+        h->acc0_clean = false;
     const size_t wtot = h->fsz * h->win;
     if (only_k >= 0)
         CU(cudaMemsetAsync(h->dAcc[obj] + h->fsz * only_k, 0, h->fsz * sizeof(double), h->st));
@@ -752,15 +754,17 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
 static int objective_fused(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
 {
     const size_t wtot = h->fsz * h->win;
-    CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
+    if (!h->acc0_clean)
+    { // afterwards every evaluation's voxel pass leaves the accumulator cleared
+        CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
+        h->acc0_clean = true;
+    }
     k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds,
                                                   h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dNcost);
     LAUNCHED(h);
-    k_reduce_partials<<<1, 1024, 0, h->st>>>(h->dPartialE, h->eval_blocks, 1, h->dOut + 2);
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->eval_blocks, h->dPartial);
     LAUNCHED(h);
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartial);
-    LAUNCHED(h);
-    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 2, h->dOut);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
     LAUNCHED(h);
     CU(cudaMemcpyAsync(h->hOut, h->dOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
