@@ -1392,7 +1392,7 @@ __global__ void k_c4(const unsigned *__restrict__ cnt, const int8_t *__restrict_
 __global__ void __launch_bounds__(128, 2)
     k_qform3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
              const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, const double *__restrict__ c4,
-             double *__restrict__ q0, double *__restrict__ q2, double *__restrict__ q3)
+             double *__restrict__ q0, double *__restrict__ q2, double *__restrict__ q3, int kmax)
 {
     extern __shared__ __align__(16) double sq[];
     const int g = threadIdx.x & 15;
@@ -1403,11 +1403,17 @@ __global__ void __launch_bounds__(128, 2)
         pidx = P - 1;
     const size_t roff = (size_t)SVD16_REC * pidx;
     const double *R[3] = {fac0 + roff, fac2 + roff, fac3 + roff};
+    // only the first kmax singular triplets (descending order) are needed: kmax columns of U (pieces 0..kmax/2*...) and of V
 #pragma unroll
     for (int o = 0; o < 3; o++)
 #pragma unroll
         for (int piece = 0; piece < 15; piece++) // 480 doubles = 240 16-byte pieces per object, 15 per lane
-            cp_async16(sg + o * 480 + 2 * (piece * 16 + g), R[o] + 2 * (piece * 16 + g));
+        {
+            const int d0 = 2 * (piece * 16 + g);          // first double of this 16-byte piece within the record
+            const int col = (d0 < 240) ? (d0 >> 4) : ((d0 - 240) >> 4); // column of U (first 240 doubles) or of V
+            if (col < kmax)
+                cp_async16(sg + o * 480 + d0, R[o] + d0);
+        }
     cp_async_commit();
     const int id = ids[pidx];
     const int r = g & 3, c = g >> 2;
@@ -1428,7 +1434,7 @@ __global__ void __launch_bounds__(128, 2)
         const double *Us = sg + o * 480, *Vs = Us + SVD16_M * SVD16_N;
         double mine = 0.0;
 #pragma unroll 1
-        for (int kk = 0; kk < SVD16_N; kk++)
+        for (int kk = 0; kk < kmax; kk++)
         {
             const double2 *v = reinterpret_cast<const double2 *>(Vs + SVD16_LDV * kk);
             double z = 0.0;
@@ -1448,7 +1454,7 @@ __global__ void __launch_bounds__(128, 2)
                 mine = val;
         }
         if (valid)
-            qd[o][(size_t)16 * pidx + g] = mine;
+            qd[o][(size_t)16 * pidx + g] = mine; // slots >= kmax are written as 0 and flagged by k_eval3 if ever needed
     }
 }
 
@@ -1457,7 +1463,8 @@ __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
-            double *__restrict__ acc0, double *__restrict__ partial, unsigned long long *__restrict__ ktot)
+            double *__restrict__ acc0, double *__restrict__ partial, unsigned long long *__restrict__ ktot, int qmax,
+            int *__restrict__ need_more_q)
 {
     // One PGURE evaluation for 16 x 15 patches and the three SVT objects U, U +- eps2*delta2.  16 lanes per patch; lane g
     // owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices and thresholds slot g of every object.
@@ -1527,6 +1534,9 @@ __global__ void __launch_bounds__(128, MINB)
         const double f2 = soft_f(sg[16 + g], sg[16 + 15], lambda, expw);
         const double f3 = soft_f(sg[32 + g], sg[32 + 15], lambda, expw);
         s4 = fma(f2, sg[64 + g], fma(f3, sg[80 + g], -2.0 * f0 * sg[48 + g]));
+        // q-forms are prepared lazily for the leading qmax triplets only; a survivor beyond them invalidates this pass
+        if (g >= qmax && (f0 != 0.0 || f2 != 0.0 || f3 != 0.0) && valid)
+            *need_more_q = 1;
     }
     unsigned m = __ballot_sync(0xffffffffu, f0 != 0.0);
     m = (m | (m >> 16)) & 0xffffu;

@@ -102,6 +102,8 @@ struct pguresvt_handle
     std::vector<double> xmax, zmax; // per resident frame
     std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
     bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false, acc0_clean = false;
+    int q_k = 0;           // number of leading triplets whose q-forms exist for the current frame
+    int *dNeedQ = nullptr; // set by k_eval3 when a triplet beyond q_k survives
     long long cur_t = -1;
     double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
@@ -287,11 +289,14 @@ static int create_impl(pguresvt_handle *h)
             return fail(PGS_ERR_UNSUPPORTED, "window of %zu voxels exceeds the fused evaluation kernel's 32-bit indexing", wtot);
         CU(cudaMalloc(&h->dC4, wtot * sizeof(double)));
         CU(cudaMalloc(&h->dPartialE, (size_t)h->eval_blocks * sizeof(double)));
+
         for (int k = 0; k < 3; k++)
             CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
     }
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
+    CU(cudaMemset(h->dOut, 0, 16 * sizeof(double)));
+    h->dNeedQ = reinterpret_cast<int *>(h->dOut + 3); // travels home with the three sums of objective_fused
     CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
     CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
@@ -708,6 +713,24 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
     return PGS_OK;
 }
 
+#define QFORM_LAZY_K 4
+static int launch_qform(pguresvt_handle *h, int kmax)
+{
+    const int smem = 8 * 3 * 480 * (int)sizeof(double);
+    if (!h->attr_qform)
+    {
+        CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        h->attr_qform = true;
+    }
+    k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dC4,
+                                                   h->dQ[0], h->dQ[1], h->dQ[2], kmax);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st)); // dOut[3] is shared with the five-sum objective
+    h->q_k = kmax;
+    return PGS_OK;
+}
+
 static int stage_count(pguresvt_handle *h, int only_k)
 {
     const size_t wtot = h->fsz * h->win;
@@ -759,15 +782,26 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
         CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
         h->acc0_clean = true;
     }
-    k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds,
-                                                  h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dNcost);
-    LAUNCHED(h);
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->eval_blocks, h->dPartial);
-    LAUNCHED(h);
-    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
-    LAUNCHED(h);
-    CU(cudaMemcpyAsync(h->hOut, h->dOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds,
+                                                      h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE,
+                                                      h->dNcost, h->q_k, h->dNeedQ);
+        LAUNCHED(h);
+        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->eval_blocks, h->dPartial);
+        LAUNCHED(h);
+        k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
+        LAUNCHED(h);
+        CU(cudaMemcpyAsync(h->hOut, h->dOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        if (!*reinterpret_cast<const int *>(h->hOut + 3))
+            break;
+        // a triplet beyond the lazily prepared q-forms survived at this lambda: prepare all of them and redo the pass
+        int rc = launch_qform(h, SVD16_N);
+        if (rc)
+            return rc;
+        h->stats[18] += 1;
+    }
     const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
     const double sigmasq = sigma * sigma;
     const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
@@ -891,18 +925,10 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         }
     }
     if (h->use_fused_eval)
-    { // bilinear forms q = u^T C4 v of every singular triplet of the three objects (see k_qform3)
+    { // bilinear forms q = u^T C4 v of the leading singular triplets of the three objects (the rest lazily, see objective_fused)
         StageTimer tm(h, 17);
-        const int smem = 8 * 3 * 480 * (int)sizeof(double);
-        if (!h->attr_qform)
-        {
-            CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            h->attr_qform = true;
-        }
-        k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N,
-                                                       h->dC4, h->dQ[0], h->dQ[1], h->dQ[2]);
-        LAUNCHED(h);
-        CU(cudaGetLastError());
+        if ((rc = launch_qform(h, QFORM_LAZY_K)))
+            return rc;
     }
     h->cur_t = t;
     return PGS_OK;
