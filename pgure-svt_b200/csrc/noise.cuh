@@ -135,28 +135,40 @@ __device__ double block_select(Get get, int n, int k, unsigned *hist, unsigned l
     return val_of(prefix);
 }
 
+// window slices analysed by one batch of launches (blockIdx.y / .z selects the entry)
+struct NoiseSliceList
+{
+    int n;
+    int idx[64]; // index of the slice inside the window cube
+};
+
 // ---- 1. split decisions ------------------------------------------------------------------------------
-// grid = (blocks per slice at this level, T); one CTA per block of side s.  flag = 1 if SplitBlockQ is true.
+// SplitBlockQ statistics: Sz = variance of the block, Se = variance of its 5-point residual (wrapping at the block's
+// own border, so the residual of a border pixel depends on the level).
+__device__ __forceinline__ double split_residual(const double *__restrict__ A, int N, int s, int y, int x)
+{
+    const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+    const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+    const double a = A[y + (size_t)N * x];
+    return (5.0 * a - (((A[yp + (size_t)N * x] + A[ym + (size_t)N * x]) + A[y + (size_t)N * xm]) + A[y + (size_t)N * xp])) / sqrt(30.0);
+}
+
+// small levels (s <= 64): grid = (blocks per slice at this level, batch entries); one CTA per block, two passes.
 template <int NT>
 __global__ void __launch_bounds__(NT) k_noise_split(const double *__restrict__ u, int N, int s, double ftest, unsigned char *__restrict__ flags,
-                              int flags_per_slice, int level_off)
+                                                    int flags_per_slice, int level_off, NoiseSliceList sl)
 {
     __shared__ double sm[NT / 32];
     const int nb = N / s;
     const int bi = blockIdx.x % nb, bj = blockIdx.x / nb;
-    const double *A = u + (size_t)N * N * blockIdx.y + (size_t)(bi * s) + (size_t)N * (bj * s);
+    const double *A = u + (size_t)N * N * sl.idx[blockIdx.y] + (size_t)(bi * s) + (size_t)N * (bj * s);
     const int R = s * s;
-    const double isq = sqrt(30.0);
     double sa = 0.0, sr = 0.0;
     for (int e = threadIdx.x; e < R; e += NT)
     {
         const int y = e % s, x = e / s;
-        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
-        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
-        const double a = A[y + (size_t)N * x];
-        const double res = (5.0 * a - (((A[yp + (size_t)N * x] + A[ym + (size_t)N * x]) + A[y + (size_t)N * xm]) + A[y + (size_t)N * xp])) / isq;
-        sa += a;
-        sr += res;
+        sa += A[y + (size_t)N * x];
+        sr += split_residual(A, N, s, y, x);
     }
     const double accuZ = block_sum<NT>(sa, sm) * (1.0 / R);
     const double accuR = block_sum<NT>(sr, sm) * (1.0 / R);
@@ -164,11 +176,7 @@ __global__ void __launch_bounds__(NT) k_noise_split(const double *__restrict__ u
     for (int e = threadIdx.x; e < R; e += NT)
     {
         const int y = e % s, x = e / s;
-        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
-        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
-        const double a = A[y + (size_t)N * x];
-        const double res = (5.0 * a - (((A[yp + (size_t)N * x] + A[ym + (size_t)N * x]) + A[y + (size_t)N * xm]) + A[y + (size_t)N * xp])) / isq;
-        const double dz = a - accuZ, de = res - accuR;
+        const double dz = A[y + (size_t)N * x] - accuZ, de = split_residual(A, N, s, y, x) - accuR;
         vz = fma(dz, dz, vz);
         ve = fma(de, de, ve);
     }
@@ -181,17 +189,189 @@ __global__ void __launch_bounds__(NT) k_noise_split(const double *__restrict__ u
     }
 }
 
+// large levels (s >= 128): a block is far too big for one CTA, so 64x64 tiles produce shifted one-pass partial sums
+// (sum (a-c), sum (a-c)^2, sum res, sum res^2; c = first pixel of the block) for every large level at once —
+// grid = (tiles per slice, large levels, batch entries) — and k_noise_split_fin folds the tiles of each block in a
+// fixed order and takes the decision.
+#define NOISE_TILE 64
+__global__ void __launch_bounds__(256) k_noise_split_tiles(const double *__restrict__ u, int N, NoiseSliceList sl, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    const int nt = N / NOISE_TILE, ti = blockIdx.x % nt, tj = blockIdx.x / nt;
+    const int s = 128 << blockIdx.y;
+    const int bi = (ti * NOISE_TILE) / s * s, bj = (tj * NOISE_TILE) / s * s;
+    const double *A = u + (size_t)N * N * sl.idx[blockIdx.z] + (size_t)bi + (size_t)N * bj;
+    const int oy = ti * NOISE_TILE - bi, ox = tj * NOISE_TILE - bj;
+    const double c = A[0];
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    for (int e = threadIdx.x; e < NOISE_TILE * NOISE_TILE; e += 256)
+    {
+        const int y = oy + (e % NOISE_TILE), x = ox + (e / NOISE_TILE);
+        const double d = A[y + (size_t)N * x] - c, r = split_residual(A, N, s, y, x);
+        q0 += d;
+        q1 = fma(d, d, q1);
+        q2 += r;
+        q3 = fma(r, r, q3);
+    }
+    const double Q0 = block_sum<256>(q0, sm), Q1 = block_sum<256>(q1, sm), Q2 = block_sum<256>(q2, sm), Q3 = block_sum<256>(q3, sm);
+    if (threadIdx.x == 0)
+    {
+        double *o = part + 4 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        o[0] = Q0, o[1] = Q1, o[2] = Q2, o[3] = Q3;
+    }
+}
+
+// grid = (blocks per slice at level s, batch entries), one warp per block
+__global__ void __launch_bounds__(32) k_noise_split_fin(const double *__restrict__ part, int N, int lvl_big, int nlev_big, double ftest,
+                                                        unsigned char *__restrict__ flags, int flags_per_slice, int level_off)
+{
+    const int s = 128 << lvl_big, nb = N / s, nt = N / NOISE_TILE, tpb = s / NOISE_TILE;
+    const int bi = blockIdx.x % nb, bj = blockIdx.x / nb;
+    const double *P = part + 4 * ((size_t)(blockIdx.y * nlev_big + lvl_big) * nt * nt);
+    double q[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < tpb * tpb; t += 32)
+    {
+        const int ti = bi * tpb + (t % tpb), tj = bj * tpb + (t / tpb);
+        const double *o = P + 4 * ((size_t)ti + (size_t)nt * tj);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            q[k] += o[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    if (threadIdx.x == 0)
+    {
+        const double R = (double)s * (double)s;
+        const double Sz = (q[1] - q[0] * q[0] / R) / (R - 1.0), Se = (q[3] - q[2] * q[2] / R) / (R - 1.0);
+        const double stat = (Sz > Se) ? Sz / Se : Se / Sz;
+        flags[(size_t)flags_per_slice * blockIdx.y + level_off + blockIdx.x] = (stat > ftest) ? 1 : 0;
+    }
+}
+
 // ---- 2. leaf statistics ------------------------------------------------------------------------------
+// Laplacian pseudo-residual of ConvolveFIR (noise.hpp:395-417) at (x, y) of an s x s region: neighbours (rows filled
+// first) times -laplacian, accumulated in column-major two-accumulator order
+__device__ __forceinline__ double laplace_residual(const double *__restrict__ A, int ld, int s, int x, int y)
+{
+    const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
+    const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
+#define IN_(a, b) A[(a) + (size_t)ld * (b)]
+    const double t0 = IN_(xm, ym) * -0.125, t1 = IN_(xm, y) * -0.125, t2 = IN_(xm, yp) * -0.125;
+    const double t3 = IN_(x, ym) * -0.125, t4 = IN_(x, y) * 1.0, t5 = IN_(x, yp) * -0.125;
+    const double t6 = IN_(xp, ym) * -0.125, t7 = IN_(xp, y) * -0.125, t8 = IN_(xp, yp) * -0.125;
+#undef IN_
+    const double v1 = (((t0 + t2) + t4) + t6) + t8;
+    const double v2 = ((t1 + t3) + t5) + t7;
+    return v1 + v2;
+}
+
+// ascending bitonic sort of 64 doubles held two per lane (element i = lane + 32 r in v_r)
+__device__ __forceinline__ void warp_sort64(double &v0, double &v1, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            if (j == 32)
+            { // k == 64: partner is the other register of the same lane, ascending
+                const double lo = fmin(v0, v1), hi = fmax(v0, v1);
+                v0 = lo, v1 = hi;
+            }
+            else
+            {
+                const double p0 = __shfl_xor_sync(0xffffffffu, v0, j), p1 = __shfl_xor_sync(0xffffffffu, v1, j);
+                const bool lower = (lane & j) == 0;
+                const bool up0 = (lane & k) == 0, up1 = ((lane + 32) & k) == 0;
+                v0 = (lower == up0) ? fmin(v0, p0) : fmax(v0, p0);
+                v1 = (lower == up1) ? fmin(v1, p1) : fmax(v1, p1);
+            }
+        }
+}
+__device__ __forceinline__ double warp_pick64(double v0, double v1, int q)
+{
+    const double a = __shfl_sync(0xffffffffu, v0, q & 31), b = __shfl_sync(0xffffffffu, v1, q & 31);
+    return (q >> 5) ? b : a;
+}
+
+// 8x8 regions (nearly all of them on noisy data): one WARP per region, two pixels per lane, everything in registers
+// — order statistics by a 64-element bitonic sort, sums by shuffles — except the 3x3 stencil, which reads a
+// 64-double shared tile.
+__global__ void __launch_bounds__(256) k_noise_leaf8(const double *__restrict__ u, int N, const NoiseRegion *__restrict__ regions,
+                                                     const int *__restrict__ list, int nlist, double *__restrict__ out)
+{
+    __shared__ double tile[8][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * 8 + wib;
+    if (w >= nlist)
+        return;
+    const int ridx = list[w];
+    const NoiseRegion rg = regions[ridx];
+    const double *A = u + (size_t)N * N * rg.slice + (size_t)rg.i + (size_t)N * rg.j;
+    // element e = y + 8 x (column-major inside the region); lane holds e = lane and e = lane + 32
+    const double a0 = A[(lane & 7) + (size_t)N * (lane >> 3)], a1 = A[(lane & 7) + (size_t)N * ((lane >> 3) + 4)];
+    tile[wib][lane] = a0;
+    tile[wib][lane + 32] = a1;
+    double s0 = a0, s1 = a1;
+    warp_sort64(s0, s1, lane);
+    const int n = 64, mq = 16; // floor((floor((n+1)/2)+1)/2)
+    const double Alo = warp_pick64(s0, s1, mq - 1), Ahi = warp_pick64(s0, s1, n - mq - 1);
+    double m = 0.0, m0 = 1E12, mprev = 0.0, inv = 0.0;
+    const double tol = 1E-6, eps = 1E-12;
+    bool first = true;
+    for (int it = 0; it < 10000; it++)
+    {
+        double w0 = 1.0, w1 = 1.0;
+        if (!first)
+        {
+            const double r0 = fabs((a0 - mprev) * inv), r1 = fabs((a1 - mprev) * inv);
+            w0 = (r0 < 0.75) ? 1.0 : 0.75 / r0;
+            w1 = (r1 < 0.75) ? 1.0 : 0.75 / r1;
+        }
+        const double S1 = warp_sum(w0 * a0 + w1 * a1), S0 = warp_sum(w0 + w1);
+        m = (fabs(S0) < eps) ? m0 : S1 / S0;
+        const double ee = warp_sum(fabs(a0 - m) + fabs(a1 - m)) / (double)n;
+        if (fabs(m0 - m) < tol || ee < tol)
+            break;
+        m0 = m;
+        const double d = ((Ahi - m) - (Alo - m)) + eps;
+        inv = 1. / d;
+        mprev = m;
+        first = false;
+    }
+    __syncwarp();
+    const double *T = tile[wib];
+    const double L0 = laplace_residual(T, 8, 8, lane >> 3, lane & 7), L1 = laplace_residual(T, 8, 8, (lane >> 3) + 4, lane & 7);
+    s0 = L0, s1 = L1;
+    warp_sort64(s0, s1, lane);
+    const double l1 = warp_pick64(s0, s1, 32), l2 = warp_pick64(s0, s1, 31);
+    const double med = l1 + (l2 - l1) / 2.0;
+    s0 = fabs(L0 - med), s1 = fabs(L1 - med);
+    warp_sort64(s0, s1, lane);
+    const double d1 = warp_pick64(s0, s1, 32), d2 = warp_pick64(s0, s1, 31);
+    const double mad = d1 + (d2 - d1) / 2.0;
+    if (lane == 0)
+    {
+        const double sig = 1.4826 * mad;
+        out[2 * (size_t)ridx] = m;
+        out[2 * (size_t)ridx + 1] = sig * sig;
+    }
+}
+
+// regions of side 16..64: one CTA each
 template <int NT>
 __global__ void __launch_bounds__(NT) k_noise_leaf(const double *__restrict__ u, int N, const NoiseRegion *__restrict__ regions,
-                             double *__restrict__ scratch, double *__restrict__ out /* 2 per region: mean, var */, int big_side)
+                                                   const int *__restrict__ list, double *__restrict__ scratch,
+                                                   double *__restrict__ out /* 2 per region: mean, var */)
 {
     __shared__ double sm[NT / 32];
     __shared__ unsigned hist[256];
     __shared__ unsigned long long spre[2];
-    const NoiseRegion rg = regions[blockIdx.x];
-    if (rg.s >= big_side)
-        return; // handled grid-wide by k_noise_big
+    const int ridx = list[blockIdx.x];
+    const NoiseRegion rg = regions[ridx];
     const int s = rg.s, n = s * s;
     const double *A = u + (size_t)N * N * rg.slice + (size_t)rg.i + (size_t)N * rg.j;
     auto getA = [&](int e) { return A[(e % s) + (size_t)N * (e / s)]; };
@@ -235,23 +415,9 @@ __global__ void __launch_bounds__(NT) k_noise_leaf(const double *__restrict__ u,
         first = false;
     }
 
-    // Laplacian pseudo-residual (ConvolveFIR, noise.hpp:395-417) into scratch
     double *L = scratch + rg.off;
     for (int e = threadIdx.x; e < n; e += NT)
-    {
-        const int y = e % s, x = e / s; // (x, y) as in the reference's loops
-        const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
-        const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
-#define IN_(a, b) A[(a) + (size_t)N * (b)]
-        // neighbours (rows filled first), multiplied by -laplacian, accumulated in column-major two-accumulator order
-        const double t0 = IN_(xm, ym) * -0.125, t1 = IN_(xm, y) * -0.125, t2 = IN_(xm, yp) * -0.125;
-        const double t3 = IN_(x, ym) * -0.125, t4 = IN_(x, y) * 1.0, t5 = IN_(x, yp) * -0.125;
-        const double t6 = IN_(xp, ym) * -0.125, t7 = IN_(xp, y) * -0.125, t8 = IN_(xp, yp) * -0.125;
-#undef IN_
-        const double v1 = (((t0 + t2) + t4) + t6) + t8;
-        const double v2 = ((t1 + t3) + t5) + t7;
-        L[e] = v1 + v2;
-    }
+        L[e] = laplace_residual(A, N, s, e / s, e % s); // (x, y) as in the reference's loops
     __syncthreads();
     auto getL = [&](int e) { return L[e]; };
     // arma::median of an even-length vector: nth = n/2, plus the largest of the lower half
@@ -265,22 +431,23 @@ __global__ void __launch_bounds__(NT) k_noise_leaf(const double *__restrict__ u,
     if (threadIdx.x == 0)
     {
         const double sig = 1.4826 * mad;
-        out[2 * (size_t)blockIdx.x] = m;
-        out[2 * (size_t)blockIdx.x + 1] = sig * sig;
+        out[2 * (size_t)ridx] = m;
+        out[2 * (size_t)ridx + 1] = sig * sig;
     }
 }
 
 // ---- grid-wide (cooperative launch) versions for the large regions and the line fit -------------------
 // Large regions (the whole-frame root node of every slice is always kept) and the ~5e5-sample line fit
 // are latency-bound inside one CTA; here the same algorithms run on one CTA per SM with grid-wide reductions:
-// per-CTA partials in a rotating slot + grid.sync, and radix-select histograms merged through a small ring of
-// global 256-bin histograms (a slot is re-zeroed one pass after it was read).
+// per-CTA partials in a rotating slot + grid.sync, and radix selects that find TWO order statistics per sweep
+// (both quartiles, or the two middle elements of a median) with histograms merged through a small ring of global
+// 2x256-bin histograms (a slot is re-zeroed one pass after it was read).
 namespace cg = cooperative_groups;
 
 struct GridScratch
 {
     double *partials; // [4][8][grid]
-    unsigned *ghist;  // [4][256], zero at launch
+    unsigned *ghist;  // [4][512], zero at launch
 };
 
 template <int NT, int NQ>
@@ -307,51 +474,66 @@ __device__ __forceinline__ void grid_sum(const double (&v)[NQ], double (&out)[NQ
     slot++;
 }
 
+// kA-th and kB-th smallest (0-based) of n values in one MSB-first radix sweep (8 bits per pass).  hist: 512 words,
+// spre: 4 words of shared memory.
 template <int NT, typename Get>
-__device__ double grid_select(Get get, int n, int k, cg::grid_group &grid, const GridScratch &gs, unsigned &hslot, unsigned *hist,
-                              unsigned long long *spre)
+__device__ void grid_select2(Get get, int n, int kA, int kB, double &outA, double &outB, cg::grid_group &grid, const GridScratch &gs,
+                             unsigned &hslot, unsigned *hist, unsigned long long *spre)
 {
-    unsigned long long prefix = 0;
-    int kk = k;
+    unsigned long long pA = 0, pB = 0;
+    int ka = kA, kb = kB;
     const int stride = gridDim.x * NT;
     for (int pass = 0; pass < 8; pass++)
     {
         const int shift = 56 - 8 * pass;
-        unsigned *G = gs.ghist + (size_t)(hslot & 3u) * 256;
-        for (int b = threadIdx.x; b < 256; b += NT)
+        const bool same = (pA == pB); // both targets still share their prefix: one histogram serves both
+        unsigned *G = gs.ghist + (size_t)(hslot & 3u) * 512;
+        for (int b = threadIdx.x; b < 512; b += NT)
             hist[b] = 0u;
         __syncthreads();
         for (int e0 = blockIdx.x * NT; e0 < n; e0 += stride)
         {
             const int e = e0 + threadIdx.x;
-            unsigned bin = 256u;
+            unsigned bin = 512u; // "does not take part"
             if (e < n)
             {
                 const unsigned long long key = key_of(get(e));
-                const bool match = (pass == 0) || (((key ^ prefix) >> (shift + 8)) == 0ull);
-                if (match)
-                    bin = (unsigned)(key >> shift) & 255u;
+                const unsigned digit = (unsigned)(key >> shift) & 255u;
+                if (pass == 0)
+                    bin = digit;
+                else
+                {
+                    const unsigned long long hi = key >> (shift + 8);
+                    if (hi == (pA >> (shift + 8)))
+                        bin = digit;
+                    else if (!same && hi == (pB >> (shift + 8)))
+                        bin = 256u + digit;
+                }
             }
             const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            if (bin < 256u && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+            if (bin < 512u && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
                 atomicAdd(&hist[bin], (unsigned)__popc(peers));
         }
         __syncthreads();
-        for (int b = threadIdx.x; b < 256; b += NT)
+        for (int b = threadIdx.x; b < 512; b += NT)
             if (hist[b])
                 atomicAdd(&G[b], hist[b]);
         grid.sync();
         // the slot read one pass ago is no longer in use by anybody: clear it for its next turn
         if (blockIdx.x == 0)
-            for (int b = threadIdx.x; b < 256; b += NT)
-                gs.ghist[(size_t)((hslot + 3u) & 3u) * 256 + b] = 0u;
-        if (threadIdx.x < 32)
-        {
+            for (int b = threadIdx.x; b < 512; b += NT)
+                gs.ghist[(size_t)((hslot + 3u) & 3u) * 512 + b] = 0u;
+        if (threadIdx.x < 64)
+        { // warp 0 resolves target A, warp 1 target B; each lane owns 8 consecutive bins
+            const int which = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const unsigned *H = G + ((which && !same) ? 256 : 0);
+            const unsigned long long prefix = which ? pB : pA;
+            const unsigned kk = (unsigned)(which ? kb : ka);
             unsigned loc[8], tot = 0;
 #pragma unroll
             for (int q = 0; q < 8; q++)
             {
-                loc[q] = G[threadIdx.x * 8 + q];
+                loc[q] = H[lane * 8 + q];
                 tot += loc[q];
             }
             unsigned inc = tot;
@@ -359,31 +541,34 @@ __device__ double grid_select(Get get, int n, int k, cg::grid_group &grid, const
             for (int o = 1; o < 32; o <<= 1)
             {
                 const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)threadIdx.x >= o)
+                if (lane >= o)
                     inc += t;
             }
-            unsigned before = inc - tot;
-            if ((unsigned)kk >= before && (unsigned)kk < inc)
+            unsigned before = inc - tot; // elements in bins of lower lanes
+            if (kk >= before && kk < inc)
             {
 #pragma unroll
                 for (int q = 0; q < 8; q++)
                 {
-                    if ((unsigned)kk >= before && (unsigned)kk < before + loc[q])
+                    if (kk >= before && kk < before + loc[q])
                     {
-                        spre[0] = prefix | ((unsigned long long)(threadIdx.x * 8 + q) << shift);
-                        spre[1] = (unsigned long long)((unsigned)kk - before);
+                        spre[2 * which] = prefix | ((unsigned long long)(lane * 8 + q) << shift);
+                        spre[2 * which + 1] = (unsigned long long)(kk - before);
                     }
                     before += loc[q];
                 }
             }
         }
         __syncthreads();
-        prefix = spre[0];
-        kk = (int)spre[1];
+        pA = spre[0];
+        ka = (int)spre[1];
+        pB = spre[2];
+        kb = (int)spre[3];
         __syncthreads();
         hslot++;
     }
-    return val_of(prefix);
+    outA = val_of(pA);
+    outB = val_of(pB);
 }
 
 // all large regions, one after the other, each spread over the whole grid.  Same maths as k_noise_leaf.
@@ -394,8 +579,8 @@ __global__ void __launch_bounds__(NT) k_noise_big(const double *__restrict__ u, 
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[NT / 32];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned long long spre[2];
+    __shared__ unsigned hist[512];
+    __shared__ unsigned long long spre[4];
     unsigned slot = 0, hslot = 0;
     const int gstride = gridDim.x * NT;
     for (int bq = 0; bq < nbig; bq++)
@@ -406,8 +591,8 @@ __global__ void __launch_bounds__(NT) k_noise_big(const double *__restrict__ u, 
         const double *A = u + (size_t)N * N * rg.slice + (size_t)rg.i + (size_t)N * rg.j;
         auto getA = [&](int e) { return A[(e & (s - 1)) + (size_t)N * (e >> sh)]; };
         const int mq = (int)floor((floor((double)((n + 1) / 2)) + 1) / 2);
-        const double Alo = grid_select<NT>(getA, n, mq - 1, grid, gs, hslot, hist, spre);
-        const double Ahi = grid_select<NT>(getA, n, n - mq - 1, grid, gs, hslot, hist, spre);
+        double Alo, Ahi;
+        grid_select2<NT>(getA, n, mq - 1, n - mq - 1, Alo, Ahi, grid, gs, hslot, hist, spre);
         double m = 0.0, m0 = 1E12, mprev = 0.0, inv = 0.0;
         const double tol = 1E-6, eps = 1E-12;
         bool first = true;
@@ -443,27 +628,14 @@ __global__ void __launch_bounds__(NT) k_noise_big(const double *__restrict__ u, 
         }
         double *L = scratch + rg.off;
         for (int e = blockIdx.x * NT + threadIdx.x; e < n; e += gstride)
-        {
-            const int y = e & (s - 1), x = e >> sh;
-            const int xp = (x + 1 == s) ? 1 : x + 1, yp = (y + 1 == s) ? 1 : y + 1;
-            const int xm = (x == 0) ? s - 2 : x - 1, ym = (y == 0) ? s - 2 : y - 1;
-#define IN_(a, b) A[(a) + (size_t)N * (b)]
-            const double t0 = IN_(xm, ym) * -0.125, t1 = IN_(xm, y) * -0.125, t2 = IN_(xm, yp) * -0.125;
-            const double t3 = IN_(x, ym) * -0.125, t4 = IN_(x, y) * 1.0, t5 = IN_(x, yp) * -0.125;
-            const double t6 = IN_(xp, ym) * -0.125, t7 = IN_(xp, y) * -0.125, t8 = IN_(xp, yp) * -0.125;
-#undef IN_
-            const double v1 = (((t0 + t2) + t4) + t6) + t8;
-            const double v2 = ((t1 + t3) + t5) + t7;
-            L[e] = v1 + v2;
-        }
+            L[e] = laplace_residual(A, N, s, e >> sh, e & (s - 1));
         grid.sync();
         auto getL = [&](int e) { return L[e]; };
-        const double l1 = grid_select<NT>(getL, n, n / 2, grid, gs, hslot, hist, spre);
-        const double l2 = grid_select<NT>(getL, n, n / 2 - 1, grid, gs, hslot, hist, spre);
+        double l1, l2, d1, d2;
+        grid_select2<NT>(getL, n, n / 2, n / 2 - 1, l1, l2, grid, gs, hslot, hist, spre);
         const double med = l1 + (l2 - l1) / 2.0;
         auto getD = [&](int e) { return fabs(L[e] - med); };
-        const double d1 = grid_select<NT>(getD, n, n / 2, grid, gs, hslot, hist, spre);
-        const double d2 = grid_select<NT>(getD, n, n / 2 - 1, grid, gs, hslot, hist, spre);
+        grid_select2<NT>(getD, n, n / 2, n / 2 - 1, d1, d2, grid, gs, hslot, hist, spre);
         const double mad = d1 + (d2 - d1) / 2.0;
         if (blockIdx.x == 0 && threadIdx.x == 0)
         {
@@ -481,8 +653,8 @@ __global__ void __launch_bounds__(NT) k_noise_wls_grid(const double *__restrict_
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[NT / 32];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned long long spre[2];
+    __shared__ unsigned hist[512];
+    __shared__ unsigned long long spre[4];
     unsigned slot = 0, hslot = 0;
     const int gstride = gridDim.x * NT;
     const double tol = 1E-6, eps = 1E-12;
@@ -530,8 +702,8 @@ __global__ void __launch_bounds__(NT) k_noise_wls_grid(const double *__restrict_
         b0 = p1;
         auto getR = [&](int e) { return Y(e) - (X(e) * p0 + p1); };
         const int mq = (int)floor((floor((double)((n + 1) / 2)) + 1) / 2);
-        const double rhi = grid_select<NT>(getR, n, n - mq - 1, grid, gs, hslot, hist, spre);
-        const double rlo = grid_select<NT>(getR, n, mq - 1, grid, gs, hslot, hist, spre);
+        double rhi, rlo;
+        grid_select2<NT>(getR, n, n - mq - 1, mq - 1, rhi, rlo, grid, gs, hslot, hist, spre);
         pd = (rhi - rlo) + eps;
         pa = p0;
         pb = p1;
@@ -569,51 +741,24 @@ __global__ void __launch_bounds__(NT) k_noise_wls_grid(const double *__restrict_
 // Per-slice results are cached: a window slice is the frame divided by the window maximum, so its quadtree and its
 // (mean, variance) samples depend only on (global frame, uMax).  Consecutive windows share 2*fw of their slices and
 // very often the maximum, so in steady state one new slice is analysed per frame; the line fit always runs over
-// the samples of all slices of the window.
+// the samples of all slices of the window.  All slices that do need analysing go through ONE batch of launches.
 struct NoiseSliceSamples
 {
     double umax = 0;
     std::vector<double> xs, ys; // robust means / variances in the reference's node order (duplicates included)
 };
 
-// device scratch of one in-flight slice analysis (own stream, so several slices overlap on the GPU while their
-// host-side quadtree walks run on separate host threads)
-struct NoiseSliceCtx
-{
-    cudaStream_t st = nullptr;
-    unsigned char *dFlags = nullptr;
-    NoiseRegion *dRegions = nullptr;
-    int *dBig = nullptr;
-    double *dScratch = nullptr, *dLeaf = nullptr, *dPartials = nullptr;
-    unsigned *dHist = nullptr;
-    size_t capFlags = 0, capRegions = 0, capScratch = 0, capBig = 0;
-    long long n_regions = 0, n_samples = 0, n_big = 0, launches = 0;
-    double t_split = 0, t_replay = 0, t_leaf = 0;
-    std::string err;
-    void release()
-    {
-        auto F = [](void *p) {
-            if (p)
-                cudaFree(p);
-        };
-        F(dFlags), F(dRegions), F(dBig), F(dScratch), F(dLeaf), F(dPartials), F(dHist);
-        if (st)
-            cudaStreamDestroy(st);
-        *this = NoiseSliceCtx();
-    }
-};
-
-#define NOISE_MAX_CTX 16
-
 struct NoiseWorkspace
 {
-    NoiseSliceCtx ctx[NOISE_MAX_CTX];
-    double *dFit = nullptr, *dPartials = nullptr, *dX = nullptr, *dY = nullptr;
+    double *dFit = nullptr, *dPartials = nullptr, *dX = nullptr, *dY = nullptr, *dSplitPart = nullptr, *dScratch = nullptr, *dLeaf = nullptr;
     unsigned *dHist = nullptr;
-    size_t capSamples = 0;
+    unsigned char *dFlags = nullptr;
+    NoiseRegion *dRegions = nullptr;
+    int *dLists = nullptr;
+    size_t capSamples = 0, capFlags = 0, capRegions = 0, capScratch = 0, capSplitPart = 0;
     int grid = 0, device = 0;
-    long long slices_analysed = 0, slices_reused = 0;
-    double fit_iters = 0, t_fit = 0, t_slices = 0;
+    long long slices_analysed = 0, slices_reused = 0, n_regions = 0, n_big = 0, n_mid = 0;
+    double fit_iters = 0, t_fit = 0, t_slices = 0, t_split = 0, t_replay = 0, t_leaf = 0;
     std::unordered_map<long long, NoiseSliceSamples> cache;
     void release()
     {
@@ -621,11 +766,10 @@ struct NoiseWorkspace
             if (p)
                 cudaFree(p);
         };
-        for (auto &c : ctx)
-            c.release();
-        F(dFit), F(dPartials), F(dHist), F(dX), F(dY);
-        dFit = dPartials = dX = dY = nullptr, dHist = nullptr;
-        capSamples = 0;
+        F(dFit), F(dPartials), F(dHist), F(dX), F(dY), F(dSplitPart), F(dScratch), F(dLeaf), F(dFlags), F(dRegions), F(dLists);
+        dFit = dPartials = dX = dY = dSplitPart = dScratch = dLeaf = nullptr, dHist = nullptr, dFlags = nullptr, dRegions = nullptr,
+        dLists = nullptr;
+        capSamples = capFlags = capRegions = capScratch = capSplitPart = 0;
         cache.clear();
     }
 };
@@ -655,6 +799,20 @@ static double noise_ftest0025(int s)
 
 #define NOISE_BIG_SIDE 128 /* regions with side >= this run grid-wide */
 
+template <typename T>
+static int noise_reserve(T *&p, size_t &cap, size_t need, std::string &err)
+{
+    if (cap >= need)
+        return 0;
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    NCU(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
 static int noise_init(NoiseWorkspace &ws, int sm_count, std::string &err)
 {
     if (ws.dFit)
@@ -663,62 +821,20 @@ static int noise_init(NoiseWorkspace &ws, int sm_count, std::string &err)
     NCU(cudaGetDevice(&ws.device));
     NCU(cudaMalloc(&ws.dFit, 8 * sizeof(double)));
     NCU(cudaMalloc(&ws.dPartials, (size_t)4 * 8 * ws.grid * sizeof(double)));
-    NCU(cudaMalloc(&ws.dHist, 4 * 256 * sizeof(unsigned)));
+    NCU(cudaMalloc(&ws.dHist, 4 * 512 * sizeof(unsigned)));
     return 0;
 }
 
-// quadtree + leaf statistics of ONE slice (N x N doubles at dA) -> samples in the reference's order.
-// big_grid: CTAs of the cooperative kernel for the large regions (fewer when several slices are in flight).
-static int noise_analyse_slice(NoiseSliceCtx &cx, const double *dA, int N, int big_grid, int full_grid, NoiseSliceSamples &outS)
+// QuadTree() (noise.hpp:419-458) of one slice replayed against its split-decision table `fl`.  Distinct kept regions
+// are appended to `regions` (slice field = `slice`); sample_region lists, in the reference's node order, the region
+// of every kept node (duplicates included).
+struct NoiseReplay
 {
-    std::string &err = cx.err;
-    cudaStream_t st = cx.st;
-    if (!st)
-    {
-        NCU(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
-        st = cx.st;
-        NCU(cudaMalloc(&cx.dPartials, (size_t)4 * 8 * full_grid * sizeof(double)));
-        NCU(cudaMalloc(&cx.dHist, 4 * 256 * sizeof(unsigned)));
-    }
-    // level table: sides N, N/2, ..., 8 (side 8 never splits but is needed to address regions)
-    std::vector<int> sides, offs;
-    int per_slice = 0, per_slice_flags = 0;
-    for (int s = N; s >= 8; s >>= 1)
-    {
-        sides.push_back(s);
-        offs.push_back(per_slice);
-        per_slice += (N / s) * (N / s);
-        if (s >= 16)
-            per_slice_flags = per_slice;
-    }
-    const size_t nflags = (size_t)per_slice_flags;
-    if (cx.capFlags < nflags)
-    {
-        if (cx.dFlags)
-            cudaFree(cx.dFlags);
-        NCU(cudaMalloc(&cx.dFlags, nflags));
-        cx.capFlags = nflags;
-    }
-    const auto tp0 = std::chrono::steady_clock::now();
-    for (size_t l = 0; l < sides.size(); l++)
-    {
-        const int s = sides[l], nb = (N / s) * (N / s);
-        if (s < 16)
-            break;
-        const double ft = noise_ftest0025(s);
-        if (s >= 128)
-            k_noise_split<1024><<<dim3(nb, 1), 1024, 0, st>>>(dA, N, s, ft, cx.dFlags, per_slice_flags, offs[l]);
-        else
-            k_noise_split<128><<<dim3(nb, 1), 128, 0, st>>>(dA, N, s, ft, cx.dFlags, per_slice_flags, offs[l]);
-        cx.launches++;
-    }
-    std::vector<unsigned char> fl(nflags);
-    NCU(cudaMemcpyAsync(fl.data(), cx.dFlags, nflags, cudaMemcpyDeviceToHost, st));
-    NCU(cudaStreamSynchronize(st));
-    const auto tp1 = std::chrono::steady_clock::now();
-    cx.t_split += std::chrono::duration<double>(tp1 - tp0).count();
-
-    // replay QuadTree() (noise.hpp:419-458) against the decision table
+    std::vector<NoiseRegion> regions;
+    std::vector<int> sample_region;
+};
+static void noise_replay(const unsigned char *fl, int N, const std::vector<int> &offs, int per_slice, int slice, NoiseReplay &out)
+{
     struct Node
     {
         int i, j, s, lvl;
@@ -727,11 +843,15 @@ static int noise_analyse_slice(NoiseSliceCtx &cx, const double *dA, int N, int b
     {
         int n, k;
     };
-    std::vector<NoiseRegion> regions;
-    std::vector<int> sample_region, big, region_of((size_t)per_slice, -1), dele;
+    std::vector<int> region_of((size_t)per_slice, -1), dele;
     std::vector<Node> tree;
     std::vector<Frame> fr;
-    long long scratch_need = 0;
+    tree.reserve((size_t)per_slice * 2 + 8);
+    dele.reserve((size_t)per_slice);
+    out.regions.clear();
+    out.sample_region.clear();
+    out.regions.reserve((size_t)(N / 8) * (N / 8) + 8);
+    out.sample_region.reserve((size_t)(N / 8) * (N / 8) * 2 + 8);
     tree.push_back({0, 0, N, 0});
     auto enter = [&](int part) {
         const Node nd = tree[part];
@@ -761,11 +881,15 @@ static int noise_analyse_slice(NoiseSliceCtx &cx, const double *dA, int N, int b
         f.k++;
         enter(part); // may push a new frame (f is not used afterwards)
     }
-    std::sort(dele.begin(), dele.end());
-    dele.erase(std::unique(dele.begin(), dele.end()), dele.end());
     std::vector<char> removed(tree.size(), 0);
-    for (size_t k = dele.size(); k-- > 1;) // k = size-1 … 1: the first entry (the root) is never shed
-        removed[dele[k]] = 1;
+    if (!dele.empty())
+    { // every split node is shed except the smallest index (the root): the reference's loop stops at k > 0
+        const int keep = *std::min_element(dele.begin(), dele.end());
+        for (int d : dele)
+            removed[d] = 1;
+        removed[keep] = 0;
+    }
+    long long scratch = 0;
     for (size_t n = 0; n < tree.size(); n++)
     {
         if (removed[n])
@@ -774,85 +898,204 @@ static int noise_analyse_slice(NoiseSliceCtx &cx, const double *dA, int N, int b
         int &ridx = region_of[offs[nd.lvl] + (nd.i / nd.s) + (N / nd.s) * (nd.j / nd.s)];
         if (ridx < 0)
         {
-            ridx = (int)regions.size();
-            regions.push_back({nd.i, nd.j, nd.s, 0, scratch_need});
-            scratch_need += (long long)nd.s * nd.s;
-            if (nd.s >= NOISE_BIG_SIDE)
-                big.push_back(ridx);
+            ridx = (int)out.regions.size();
+            out.regions.push_back({nd.i, nd.j, nd.s, slice, nd.s > 8 ? scratch : -1});
+            if (nd.s > 8)
+                scratch += (long long)nd.s * nd.s; // Laplacian scratch (8x8 regions keep theirs on chip); rebased by the caller
         }
-        sample_region.push_back(ridx);
+        out.sample_region.push_back(ridx);
     }
-    const auto tp2 = std::chrono::steady_clock::now();
-    cx.t_replay += std::chrono::duration<double>(tp2 - tp1).count();
-    const size_t nreg = regions.size(), nbig = big.size();
-    cx.n_regions += (long long)nreg;
-    cx.n_samples += (long long)sample_region.size();
-    cx.n_big += (long long)nbig;
-    if (cx.capRegions < nreg)
+}
+
+// quadtree + leaf statistics of a batch of window slices (indices `todo` into dU) -> samples in the reference's order
+static int noise_analyse_batch(NoiseWorkspace &ws, const double *dU, int N, const std::vector<int> &todo,
+                               const std::vector<NoiseSliceSamples *> &parts, cudaStream_t st, long long *launches, std::string &err)
+{
+    const int S = (int)todo.size();
+    NoiseSliceList sl;
+    sl.n = S;
+    for (int q = 0; q < S; q++)
+        sl.idx[q] = todo[q];
+    // level table: sides N, N/2, ..., 8 (side 8 never splits but is needed to address regions)
+    std::vector<int> sides, offs;
+    int per_slice = 0, per_slice_flags = 0;
+    for (int s = N; s >= 8; s >>= 1)
     {
-        if (cx.dRegions)
-            cudaFree(cx.dRegions);
-        if (cx.dLeaf)
-            cudaFree(cx.dLeaf);
-        NCU(cudaMalloc(&cx.dRegions, nreg * sizeof(NoiseRegion)));
-        NCU(cudaMalloc(&cx.dLeaf, nreg * 2 * sizeof(double)));
-        cx.capRegions = nreg;
+        sides.push_back(s);
+        offs.push_back(per_slice);
+        per_slice += (N / s) * (N / s);
+        if (s >= 16)
+            per_slice_flags = per_slice;
     }
-    if (cx.capScratch < (size_t)scratch_need)
+    const size_t nflags = (size_t)per_slice_flags * S;
+    int rc;
+    if ((rc = noise_reserve(ws.dFlags, ws.capFlags, nflags, err)))
+        return rc;
+    const auto tp0 = std::chrono::steady_clock::now();
+    int nlev_big = 0;
+    for (int s = 128; s <= N; s <<= 1)
+        nlev_big++;
+    if (nlev_big)
     {
-        if (cx.dScratch)
-            cudaFree(cx.dScratch);
-        NCU(cudaMalloc(&cx.dScratch, (size_t)scratch_need * sizeof(double)));
-        cx.capScratch = (size_t)scratch_need;
+        const int nt = N / NOISE_TILE;
+        if ((rc = noise_reserve(ws.dSplitPart, ws.capSplitPart, (size_t)4 * S * nlev_big * nt * nt, err)))
+            return rc;
+        k_noise_split_tiles<<<dim3(nt * nt, nlev_big, S), 256, 0, st>>>(dU, N, sl, ws.dSplitPart);
+        if (launches)
+            (*launches)++;
     }
-    if (cx.capBig < nbig)
+    for (size_t l = 0; l < sides.size(); l++)
     {
-        if (cx.dBig)
-            cudaFree(cx.dBig);
-        NCU(cudaMalloc(&cx.dBig, nbig * sizeof(int)));
-        cx.capBig = nbig;
+        const int s = sides[l], nb = (N / s) * (N / s);
+        if (s < 16)
+            break;
+        const double ft = noise_ftest0025(s);
+        if (s >= 128)
+        {
+            int lb = 0;
+            while ((128 << lb) < s)
+                lb++;
+            k_noise_split_fin<<<dim3(nb, S), 32, 0, st>>>(ws.dSplitPart, N, lb, nlev_big, ft, ws.dFlags, per_slice_flags, offs[l]);
+        }
+        else
+            k_noise_split<128><<<dim3(nb, S), 128, 0, st>>>(dU, N, s, ft, ws.dFlags, per_slice_flags, offs[l], sl);
+        if (launches)
+            (*launches)++;
     }
-    NCU(cudaMemcpyAsync(cx.dRegions, regions.data(), nreg * sizeof(NoiseRegion), cudaMemcpyHostToDevice, st));
-    NCU(cudaMemcpyAsync(cx.dBig, big.data(), nbig * sizeof(int), cudaMemcpyHostToDevice, st));
-    // small regions: one CTA each (large ones return immediately inside the kernel)
-    k_noise_leaf<128><<<(unsigned)nreg, 128, 0, st>>>(dA, N, cx.dRegions, cx.dScratch, cx.dLeaf, NOISE_BIG_SIDE);
-    cx.launches++;
-    {
-        GridScratch gs;
-        gs.partials = cx.dPartials;
-        gs.ghist = cx.dHist;
-        NCU(cudaMemsetAsync(cx.dHist, 0, 4 * 256 * sizeof(unsigned), st));
-        const double *a0 = dA;
-        int a1 = N, a4 = (int)nbig;
-        const NoiseRegion *a2 = cx.dRegions;
-        const int *a3 = cx.dBig;
-        double *a5 = cx.dScratch, *a6 = cx.dLeaf;
-        void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
-        NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(big_grid), dim3(512), args, 0, st));
-        cx.launches++;
-    }
-    std::vector<double> leaf(nreg * 2);
-    NCU(cudaMemcpyAsync(leaf.data(), cx.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned char> fl(nflags);
+    NCU(cudaMemcpyAsync(fl.data(), ws.dFlags, nflags, cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
-    cx.t_leaf += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp2).count();
-    outS.xs.clear();
-    outS.ys.clear();
-    outS.xs.reserve(sample_region.size());
-    outS.ys.reserve(sample_region.size());
-    for (int r : sample_region)
-    { // means and variances are filtered independently with >= 0 (noise.hpp:103-104)
-        const double mm = leaf[2 * (size_t)r], vv = leaf[2 * (size_t)r + 1];
-        if (mm >= 0.)
-            outS.xs.push_back(mm);
-        if (vv >= 0.)
-            outS.ys.push_back(vv);
+    const auto tp1 = std::chrono::steady_clock::now();
+    ws.t_split += std::chrono::duration<double>(tp1 - tp0).count();
+
+    // replay QuadTree() against the decision tables (host, one thread per slice when there are several)
+    std::vector<NoiseReplay> rep(S);
+    {
+        auto work = [&](int w, int nw) {
+            for (int q = w; q < S; q += nw)
+                noise_replay(fl.data() + (size_t)per_slice_flags * q, N, offs, per_slice, todo[q], rep[q]);
+        };
+        const int nw = std::min(S, 16);
+        if (nw <= 1)
+            work(0, 1);
+        else
+        {
+            std::vector<std::thread> th;
+            for (int w = 0; w < nw; w++)
+                th.emplace_back(work, w, nw);
+            for (auto &t : th)
+                t.join();
+        }
+    }
+    // concatenate: region index base and scratch base per slice; lists of 8x8 / mid / big regions
+    std::vector<size_t> rbase(S + 1, 0);
+    for (int q = 0; q < S; q++)
+        rbase[q + 1] = rbase[q] + rep[q].regions.size();
+    const size_t nreg = rbase[S];
+    std::vector<NoiseRegion> regions(nreg);
+    std::vector<int> l8, lmid, lbig;
+    l8.reserve(nreg);
+    long long scratch_need = 0;
+    for (int q = 0; q < S; q++)
+        for (size_t r = 0; r < rep[q].regions.size(); r++)
+        {
+            NoiseRegion rg = rep[q].regions[r];
+            const int gi = (int)(rbase[q] + r);
+            if (rg.s == 8)
+                l8.push_back(gi);
+            else
+            {
+                rg.off = scratch_need;
+                scratch_need += (long long)rg.s * rg.s;
+                (rg.s >= NOISE_BIG_SIDE ? lbig : lmid).push_back(gi);
+            }
+            regions[gi] = rg;
+        }
+    const auto tp2 = std::chrono::steady_clock::now();
+    ws.t_replay += std::chrono::duration<double>(tp2 - tp1).count();
+    ws.n_regions += (long long)nreg;
+    ws.n_big += (long long)lbig.size();
+    ws.n_mid += (long long)lmid.size();
+    {
+        const size_t old = ws.capRegions;
+        if ((rc = noise_reserve(ws.dRegions, ws.capRegions, nreg, err)))
+            return rc;
+        if (ws.capRegions != old)
+        { // out (2 doubles) and list entries (1 int) per region travel with the region table
+            if (ws.dLeaf)
+                cudaFree(ws.dLeaf);
+            if (ws.dLists)
+                cudaFree(ws.dLists);
+            ws.dLeaf = nullptr, ws.dLists = nullptr;
+            NCU(cudaMalloc(&ws.dLeaf, ws.capRegions * 2 * sizeof(double)));
+            NCU(cudaMalloc(&ws.dLists, ws.capRegions * sizeof(int)));
+        }
+    }
+    if ((rc = noise_reserve(ws.dScratch, ws.capScratch, (size_t)std::max<long long>(scratch_need, 1), err)))
+        return rc;
+    std::vector<int> lists;
+    lists.reserve(nreg);
+    lists.insert(lists.end(), l8.begin(), l8.end());
+    lists.insert(lists.end(), lmid.begin(), lmid.end());
+    lists.insert(lists.end(), lbig.begin(), lbig.end());
+    NCU(cudaMemcpyAsync(ws.dRegions, regions.data(), nreg * sizeof(NoiseRegion), cudaMemcpyHostToDevice, st));
+    NCU(cudaMemcpyAsync(ws.dLists, lists.data(), nreg * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int *d8 = ws.dLists, *dMid = ws.dLists + l8.size(), *dBig = dMid + lmid.size();
+    if (!l8.empty())
+    {
+        k_noise_leaf8<<<(unsigned)((l8.size() + 7) / 8), 256, 0, st>>>(dU, N, ws.dRegions, d8, (int)l8.size(), ws.dLeaf);
+        if (launches)
+            (*launches)++;
+    }
+    if (!lmid.empty())
+    {
+        k_noise_leaf<128><<<(unsigned)lmid.size(), 128, 0, st>>>(dU, N, ws.dRegions, dMid, ws.dScratch, ws.dLeaf);
+        if (launches)
+            (*launches)++;
+    }
+    if (!lbig.empty())
+    {
+        GridScratch gs;
+        gs.partials = ws.dPartials;
+        gs.ghist = ws.dHist;
+        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 512 * sizeof(unsigned), st));
+        const double *a0 = dU;
+        int a1 = N, a4 = (int)lbig.size();
+        const NoiseRegion *a2 = ws.dRegions;
+        const int *a3 = dBig;
+        double *a5 = ws.dScratch, *a6 = ws.dLeaf;
+        void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
+        NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(ws.grid), dim3(512), args, 0, st));
+        if (launches)
+            (*launches)++;
+    }
+    std::vector<double> leaf(nreg * 2);
+    NCU(cudaMemcpyAsync(leaf.data(), ws.dLeaf, nreg * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NCU(cudaStreamSynchronize(st));
+    NCU(cudaGetLastError());
+    ws.t_leaf += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp2).count();
+    for (int q = 0; q < S; q++)
+    {
+        NoiseSliceSamples &o = *parts[todo[q]];
+        o.xs.clear();
+        o.ys.clear();
+        o.xs.reserve(rep[q].sample_region.size());
+        o.ys.reserve(rep[q].sample_region.size());
+        for (int r : rep[q].sample_region)
+        { // means and variances are filtered independently with >= 0 (noise.hpp:103-104)
+            const double mm = leaf[2 * (rbase[q] + (size_t)r)], vv = leaf[2 * (rbase[q] + (size_t)r) + 1];
+            if (mm >= 0.)
+                o.xs.push_back(mm);
+            if (vv >= 0.)
+                o.ys.push_back(vv);
+        }
     }
     return 0;
 }
 
 // Estimate (alpha, mu, sigma) of one window dU (N,N,T) whose slice k is global frame frame0+k divided by umax.
-// In/out values < 0 are estimated (noise.hpp:113-147).
+// In/out values < 0 are estimated (noise.hpp:113-147).  Everything runs on stream `st`.
 static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, int T, int method, int sm_count, cudaStream_t st,
                                  double &alpha, double &mu, double &sigma, long long *launches, std::string &err,
                                  long long frame0 = -1, double umax = 0.0)
@@ -895,45 +1138,12 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
     }
     if (!todo.empty())
     {
-        // the window cube was produced on `st`: make it visible to the per-slice streams
-        NCU(cudaStreamSynchronize(st));
         const auto ts0 = std::chrono::steady_clock::now();
-        const int nthreads = (int)std::min<size_t>(todo.size(), NOISE_MAX_CTX);
-        const int big_grid = std::max(8, ws.grid / nthreads);
-        std::vector<int> rcs(nthreads, 0);
-        auto worker = [&](int w) {
-            cudaSetDevice(ws.device);
-            for (size_t q = (size_t)w; q < todo.size(); q += (size_t)nthreads)
-            {
-                const int k = todo[q];
-                const int r = noise_analyse_slice(ws.ctx[w], dU + (size_t)N * N * k, N, big_grid, ws.grid, *parts[k]);
-                if (r)
-                {
-                    rcs[w] = r;
-                    return;
-                }
-            }
-        };
-        if (nthreads == 1)
-            worker(0);
-        else
+        for (size_t b = 0; b < todo.size(); b += 64)
         {
-            std::vector<std::thread> th;
-            for (int w = 0; w < nthreads; w++)
-                th.emplace_back(worker, w);
-            for (auto &t : th)
-                t.join();
-        }
-        for (int w = 0; w < nthreads; w++)
-        {
-            if (launches)
-                *launches += ws.ctx[w].launches;
-            ws.ctx[w].launches = 0;
-            if (rcs[w])
-            {
-                err = ws.ctx[w].err;
-                return rcs[w];
-            }
+            const std::vector<int> chunk(todo.begin() + b, todo.begin() + std::min(todo.size(), b + 64));
+            if ((rc = noise_analyse_batch(ws, dU, N, chunk, parts, st, launches, err)))
+                return rc;
         }
         ws.slices_analysed += (long long)todo.size();
         ws.t_slices += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
@@ -963,17 +1173,20 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
             cudaFree(ws.dX);
         if (ws.dY)
             cudaFree(ws.dY);
+        ws.dX = ws.dY = nullptr;
+        ws.capSamples = 0;
         NCU(cudaMalloc(&ws.dX, n * sizeof(double)));
         NCU(cudaMalloc(&ws.dY, n * sizeof(double)));
         ws.capSamples = n;
     }
+    const auto tf0 = std::chrono::steady_clock::now();
     NCU(cudaMemcpyAsync(ws.dX, xs.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
     NCU(cudaMemcpyAsync(ws.dY, ys.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
     {
         GridScratch gs;
         gs.partials = ws.dPartials;
         gs.ghist = ws.dHist;
-        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 256 * sizeof(unsigned), st));
+        NCU(cudaMemsetAsync(ws.dHist, 0, 4 * 512 * sizeof(unsigned), st));
         const double *a0 = ws.dX, *a1 = ws.dY;
         int a2 = (int)n;
         double *a3 = ws.dFit;
@@ -983,15 +1196,17 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
             (*launches)++;
     }
     double fit[4];
-    const auto tf0 = std::chrono::steady_clock::now();
     NCU(cudaMemcpyAsync(fit, ws.dFit, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     NCU(cudaStreamSynchronize(st));
     NCU(cudaGetLastError());
     ws.t_fit += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
     ws.fit_iters = fit[2];
     if (getenv("PGURESVT_NOISE_TIMING"))
-        fprintf(stderr, "[noise] slices %.2f ms (analysed %lld, reused %lld), fit %.2f ms (%g iters), %zu samples\n", ws.t_slices * 1e3,
-                ws.slices_analysed, ws.slices_reused, ws.t_fit * 1e3, ws.fit_iters, n);
+        fprintf(stderr,
+                "[noise] slices %.2f ms (analysed %lld, reused %lld; split %.2f, replay %.2f, leaves %.2f ms; regions %lld, mid %lld, big %lld), "
+                "fit %.2f ms (%g iters), %zu samples\n",
+                ws.t_slices * 1e3, ws.slices_analysed, ws.slices_reused, ws.t_split * 1e3, ws.t_replay * 1e3, ws.t_leaf * 1e3, ws.n_regions,
+                ws.n_mid, ws.n_big, ws.t_fit * 1e3, ws.fit_iters, n);
     alpha = (alpha >= 0.) ? alpha : fit[0]; // noise.hpp:113
     if (method >= 1 && method <= 3)
     {
