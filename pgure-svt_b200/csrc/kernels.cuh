@@ -1012,6 +1012,34 @@ __device__ __forceinline__ void jacobi_cs_fast(double A, double B, double G, dou
     s = rot ? cc * t : 0.0;
 }
 
+// Rotation for a slot pair whose squared norms A, B are TRACKED (updated after every rotation instead of being
+// recomputed from the columns).  The tangent only steers convergence, so it is taken from the unrefined MUFU seeds
+// (~2^-20 relative): a rotation then shrinks the pair's cosine by ~1e-6 instead of annihilating it, which the
+// quadratically convergent end game does not notice.  The rotation itself stays orthonormal to rounding because
+// c = 1/sqrt(1+t^2) is refined to full precision and s = c t.  w is the exchange of squared norm for ANY orthonormal
+// (c, s):  A' = c^2 A - 2 c s G + s^2 B = A + w,  B' = B - w  with  w = s (s (B - A) - 2 c G).
+__device__ __forceinline__ void jacobi_cs_track(double &A, double &B, double G, double tol2, double big2, double &c, double &s,
+                                                bool &big)
+{
+    const double g2 = G * G, ab = A * B;
+    const bool rot = g2 > tol2 * ab;
+    big = big || (g2 > big2 * ab);
+    const double d = B - A;
+    const double q = fma(d, d, 4.0 * g2);
+    double rq, rd;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rq) : "d"(q));
+    const double den = fma(q, rq, fabs(d)); // |d| + sqrt(d^2 + 4 G^2)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
+    const double G2 = G + G;
+    const double t = ((d >= 0.0) ? G2 : -G2) * rd;
+    const double cc = rsqrt_fast(fma(t, t, 1.0));
+    c = rot ? cc : 1.0;
+    s = rot ? cc * t : 0.0;
+    const double w = s * fma(s, d, -c * G2);
+    A += w;
+    B -= w;
+}
+
 // transposing reduction of 8 values over the 4 lanes of a group: lane `sub` gets the sums of x[2*sub], x[2*sub+1]
 __device__ __forceinline__ void tr4_8(const double (&x)[8], int sub, double &o0, double &o1)
 {
@@ -1067,7 +1095,7 @@ __device__ __forceinline__ void cp_async_wait()
 
 #define SVD16_V0_STRIDE 242 /* doubles per matrix in shared memory: 15 x 16 + 2 padding (bank spread) */
 
-template <int WARM>
+template <int WARM, int TRACK>
 __global__ void __launch_bounds__(128, 2)
     k_svd16_l4(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
                int vecSize, int N, double *__restrict__ fac, const double *__restrict__ fac0, int max_sweeps, double tol2,
@@ -1143,38 +1171,83 @@ __global__ void __launch_bounds__(128, 2)
     }
 
     int sweep = 0;
+    double nr[4] = {0.0, 0.0, 0.0, 0.0}; // TRACK: squared norms of slots 4*sub .. 4*sub+3
 #pragma unroll 1
     for (; sweep < max_sweeps;)
     {
         bool big = false;
+        if (TRACK)
+        { // fresh squared norms at the start of every sweep (the updates below drift by rounding only)
+            double n2s[16];
+            n2s[0] = 0.0;
+#pragma unroll
+            for (int j = 1; j < 16; j++)
+            {
+                double sacc = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    sacc = fma(a[r][j], a[r][j], sacc);
+                n2s[j] = sacc;
+            }
+            tr4_16(n2s, sub, nr);
+        }
 #pragma unroll 1
         for (int round = 0; round < 15; round++)
         {
-            double pa[8], pb[8], pg[8];
-            pa[0] = pb[0] = pg[0] = 0.0;
-#pragma unroll
-            for (int i = 1; i < 8; i++)
-            {
-                double sa = 0.0, sb = 0.0, sg = 0.0;
-#pragma unroll
-                for (int r = 0; r < 4; r++)
-                {
-                    const double x = a[r][2 * i], y = a[r][2 * i + 1];
-                    sa = fma(x, x, sa);
-                    sb = fma(y, y, sb);
-                    sg = fma(x, y, sg);
-                }
-                pa[i] = sa;
-                pb[i] = sb;
-                pg[i] = sg;
-            }
-            double A0, A1, B0, B1, G0, G1;
-            tr4_8(pa, sub, A0, A1);
-            tr4_8(pb, sub, B0, B1);
-            tr4_8(pg, sub, G0, G1);
             double c0, s0, c1, s1;
-            jacobi_cs_fast(A0, B0, G0, tol2, big2, c0, s0, big);
-            jacobi_cs_fast(A1, B1, G1, tol2, big2, c1, s1, big);
+            if (TRACK)
+            {
+                double pg[8];
+                pg[0] = 0.0;
+#pragma unroll
+                for (int i = 1; i < 8; i++)
+                {
+                    double sg = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        sg = fma(a[r][2 * i], a[r][2 * i + 1], sg);
+                    pg[i] = sg;
+                }
+                double G0, G1;
+                tr4_8(pg, sub, G0, G1);
+                jacobi_cs_track(nr[0], nr[1], G0, tol2, big2, c0, s0, big);
+                jacobi_cs_track(nr[2], nr[3], G1, tol2, big2, c1, s1, big);
+                // the norms travel with their columns (RR_MOVE below): slot 4s <- 4s-2, 4s+2 <- 4s, 4s+1 <- 4s+3, 4s+3 <- 4s+5
+                const double up = __shfl_up_sync(0xffffffffu, nr[2], 1, 4);
+                const double dn = __shfl_down_sync(0xffffffffu, nr[1], 1, 4);
+                const double o0 = nr[0], o1 = nr[1], o2 = nr[2], o3 = nr[3];
+                nr[0] = (sub == 0) ? 0.0 : up;
+                nr[1] = o3;
+                nr[2] = (sub == 0) ? o1 : o0;
+                nr[3] = (sub == 3) ? o2 : dn;
+            }
+            else
+            {
+                double pa[8], pb[8], pg[8];
+                pa[0] = pb[0] = pg[0] = 0.0;
+#pragma unroll
+                for (int i = 1; i < 8; i++)
+                {
+                    double sa = 0.0, sb = 0.0, sg = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                    {
+                        const double x = a[r][2 * i], y = a[r][2 * i + 1];
+                        sa = fma(x, x, sa);
+                        sb = fma(y, y, sb);
+                        sg = fma(x, y, sg);
+                    }
+                    pa[i] = sa;
+                    pb[i] = sb;
+                    pg[i] = sg;
+                }
+                double A0, A1, B0, B1, G0, G1;
+                tr4_8(pa, sub, A0, A1);
+                tr4_8(pb, sub, B0, B1);
+                tr4_8(pg, sub, G0, G1);
+                jacobi_cs_fast(A0, B0, G0, tol2, big2, c0, s0, big);
+                jacobi_cs_fast(A1, B1, G1, tol2, big2, c1, s1, big);
+            }
 #pragma unroll
             for (int i = 1; i < 8; i++)
             {

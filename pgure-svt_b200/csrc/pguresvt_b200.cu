@@ -248,7 +248,7 @@ static int create_impl(pguresvt_handle *h)
     h->use_reg_svd = (h->m == 16 && h->n == 15 && p.svd_kernel != 1);
     if (p.svd_kernel >= 2 && !h->use_reg_svd)
         return fail(PGS_ERR_UNSUPPORTED, "register SVD kernels only cover 16x15 Casorati matrices");
-    h->use_l4 = h->use_reg_svd && p.svd_kernel != 2;
+    h->use_l4 = h->use_reg_svd && p.svd_kernel != 2; // 0 / 3: 4-lane kernel with tracked / recomputed pair norms
     h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
     {
         const double kappa = 1.;
@@ -693,19 +693,22 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
     {
         const long long nthreads = (long long)h->P * 4;
         const double big = 1e-6, big2 = big * big;
+        const bool track = h->p.svd_kernel != 3; // 3: legacy variant that recomputes the pair norms every round
+        auto cold = track ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
+        auto warm = track ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
         if (obj == 0)
-            k_svd16_l4<0><<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
-                                                                  nullptr, max_sweeps, tol2, big2, h->dSweeps);
+            cold<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
+                                                         max_sweeps, tol2, big2, h->dSweeps);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
         {
             const int smem_warm = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
             if (!h->attr_warm)
             { // per device: the handle is bound to one device
-                CU(cudaFuncSetAttribute(k_svd16_l4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
+                CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
                 h->attr_warm = true;
             }
-            k_svd16_l4<1><<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
-                                                                  h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
+            warm<<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
+                                                         h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
         }
     }
     else if (h->use_reg_svd)
