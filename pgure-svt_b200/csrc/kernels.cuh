@@ -1572,13 +1572,14 @@ __global__ void __launch_bounds__(128, MINB)
         cp_async16(sg + 64 + h2, q2 + (size_t)16 * pidx + h2);
         cp_async16(sg + 80 + h2, q3 + (size_t)16 * pidx + h2);
     }
+    // chunk 0 is the leading triplet alone (on typical data it is the only survivor), later chunks hold EV_C triplets
     auto request_chunk = [&](int c0, int buf) {
         double *dst = sg + 96 + buf * EV_CH;
 #pragma unroll
         for (int c = 0; c < EV_C; c++)
         {
             const int kk = c0 + c;
-            if (kk < SVD16_N)
+            if (kk < SVD16_N && (c0 > 0 || c == 0))
             {
                 // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
                 const double *src = (g < 8) ? R0 + SVD16_M * kk + 2 * g : R0 + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
@@ -1619,17 +1620,18 @@ __global__ void __launch_bounds__(128, MINB)
     for (int k = 0; k < SVD16_N; k++)
         a0[k] = 0.0;
     int buf = 0;
-    for (int c0 = 0; c0 < Kw; c0 += EV_C)
+    for (int c0 = 0; c0 < Kw; c0 += (c0 ? EV_C : 1))
     {
-        if (c0 + EV_C < Kw)
-            request_chunk(c0 + EV_C, buf ^ 1);
+        const int nxt = c0 ? c0 + EV_C : 1;
+        if (nxt < Kw)
+            request_chunk(nxt, buf ^ 1);
         cp_async_commit();
         const double *cb = sg + 96 + buf * EV_CH;
 #pragma unroll
         for (int cc = 0; cc < EV_C; cc++)
         {
             const int kk = c0 + cc;
-            if (kk < Kw)
+            if (kk < Kw && (c0 > 0 || cc == 0))
             {
                 const double fk0 = __shfl_sync(0xffffffffu, f0, (lane & 16) | kk);
                 const double *b0 = cb + cc * 32;

@@ -4,6 +4,8 @@
 //   * plain HBM copy bandwidth for cross-checking MEASURED_PEAKS.json.
 // Prints one JSON object.  nvcc -O3 -gencode arch=compute_100a,code=sm_100a microbench.cu -o ../microbench
 #include <cstdio>
+#include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 __global__ void k_dfma(double *out, int iters)
@@ -39,6 +41,38 @@ __global__ void k_atomic_patch(T *acc, int N, int reps)
         const int yy = min(max(y + ((int)(patch * 7 + k) % 5) - 2, 0), M1 - 1);
         const size_t vox = (size_t)(yy + (g & 3)) + (size_t)N * (x + (g >> 2)) + (size_t)N * N * k;
         atomicAdd(acc + vox, (T)1);
+    }
+}
+// The same overlap-add pattern through the TMA: every patch slice is one 4 x 4 x 1 box of a 3-D FP64 tensor map,
+// added to global memory with cp.reduce.async.bulk.tensor (arbitrary element coordinates, no 16-byte alignment
+// requirement on the destination).  16 lanes per patch stage the 15 boxes in shared memory, lanes 0..14 issue one box each.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_tma_patch(const __grid_constant__ CUtensorMap tmap, int N, int reps)
+{
+    __shared__ __align__(128) double sbox[8][15][16];
+    const int g = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const size_t patch = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int M1 = N - 3;
+    const int y = (int)(patch % M1), x = (int)((patch / M1) % M1);
+    for (int k = 0; k < reps; k++)
+        sbox[grp][k][g] = 1.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (g < reps)
+    {
+        const int k = g;
+        const int yy = min(max(y + ((int)(patch * 7 + k) % 5) - 2, 0), M1 - 1);
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&sbox[grp][k][0]);
+        if (MODE == 2)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(yy),
+                         "r"(x), "r"(k), "r"(sa)
+                         : "memory");
+        else
+            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap),
+                         "r"(yy), "r"(x), "r"(k), "r"(sa)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 __global__ void k_copy(const double4 *a, double4 *b, size_t n)
@@ -120,6 +154,70 @@ int main()
             patch_g[v] = np * 16.0 * 15 / (ms * 1e-3) / 1e9;
         }
     }
+    // TMA reduce-add variant of the patch pattern
+    double tma_g = 0, tma_mode_g[3] = {0, 0, 0};
+    const char *tma_err = "ok";
+    {
+        const int N = 1024;
+        typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            tma_err = "no cuTensorMapEncodeTiled";
+        else
+        {
+            for (int mode = 2; mode >= 0; mode--)
+            {
+                CUtensorMap tm;
+                cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)N, 15};
+                cuuint64_t strides[2] = {(cuuint64_t)N * 8, (cuuint64_t)N * N * 8};
+                cuuint32_t box[3] = {4, 4, 1};
+                cuuint32_t estr[3] = {1, 1, 1};
+                CUresult r = ((encode_t)fn)(&tm, mode == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, acc, dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS)
+                {
+                    tma_err = "encode failed";
+                    continue;
+                }
+                const size_t np = (size_t)(N - 3) * (N - 3);
+                const unsigned blocks = (unsigned)((np * 16 + 127) / 128);
+                cudaMemset(acc, 0, n * sizeof(double));
+                for (int rep = 0; rep < 2; rep++)
+                {
+                    cudaEventRecord(e0);
+                    if (mode == 0) k_tma_patch<0><<<blocks, 128>>>(tm, N, 15);
+                    if (mode == 1) k_tma_patch<1><<<blocks, 128>>>(tm, N, 15);
+                    if (mode == 2) k_tma_patch<2><<<blocks, 128>>>(tm, N, 15);
+                    cudaEventRecord(e1);
+                }
+                float ms = timeit(e0, e1);
+                cudaError_t ce = cudaDeviceSynchronize();
+                fprintf(stderr, "tma mode %d: %.3f ms, %s\n", mode, ms, cudaGetErrorString(ce));
+                if (ce != cudaSuccess)
+                {
+                    tma_err = "kernel failed";
+                    break;
+                }
+                tma_mode_g[mode] = np * 16.0 * 15 / (ms * 1e-3) / 1e9;
+                if (mode == 0)
+                {
+                    tma_g = tma_mode_g[0];
+                    double *hacc = (double *)malloc(n * sizeof(double));
+                    cudaMemcpy(hacc, acc, n * sizeof(double), cudaMemcpyDeviceToHost);
+                    double tot = 0;
+                    for (size_t i = 0; i < n; i++)
+                        tot += hacc[i];
+                    free(hacc);
+                    if (tot != 2.0 * np * 240.0)
+                        tma_err = "sum mismatch";
+                }
+            }
+        }
+    }
     // copy
     size_t cn = (size_t)1 << 27; // 128M double4 = 4 GB
     double4 *a, *b;
@@ -138,7 +236,7 @@ int main()
     }
     printf("{\"dfma_tflops\": %.2f, \"dfma_tflops_sustained\": %.2f, \"atomic_f64_gops_coalesced\": %.1f, "
            "\"atomic_f64_gops_strided\": %.1f, \"patch_red_f64_gops\": %.1f, \"patch_red_u64_gops\": %.1f, \"patch_red_f32_gops\": %.1f, "
-           "\"copy_gbs\": %.1f, \"cuda_error\": \"%s\"}\n",
-           best, sustained, atom_g[0], atom_g[1], patch_g[0], patch_g[1], patch_g[2], copy, cudaGetErrorString(cudaGetLastError()));
+           "\"patch_tma_reduce_f64_gops\": %.1f, \"tma\": \"%s\", \"patch_tma_u64_gops\": %.1f, \"patch_tma_store_gops\": %.1f, \"copy_gbs\": %.1f, \"cuda_error\": \"%s\"}\n",
+           best, sustained, atom_g[0], atom_g[1], patch_g[0], patch_g[1], patch_g[2], tma_g, tma_err, tma_mode_g[1], tma_mode_g[2], copy, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -693,9 +693,12 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
     {
         const long long nthreads = (long long)h->P * 4;
         const double big = 1e-6, big2 = big * big;
-        const bool track = h->p.svd_kernel != 3; // 3: legacy variant that recomputes the pair norms every round
-        auto cold = track ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
-        auto warm = track ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
+        // 0: tracked pair norms; 3: legacy variant that recomputes the pair norms every round
+        // (unrolling the 15 rounds removes the register moves of the round-robin permutation but the loop then outgrows
+        //  the instruction cache: measured 1.15x (3 rounds) to 1.7x (15 rounds) slower on B200)
+        const int variant = h->p.svd_kernel == 3 ? 0 : 1;
+        auto cold = variant == 1 ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
+        auto warm = variant == 1 ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
         if (obj == 0)
             cold<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
                                                          max_sweeps, tol2, big2, h->dSweeps);
@@ -809,9 +812,11 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     }
     for (int attempt = 0; attempt < 2; attempt++)
     {
-        k_eval3<4><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds,
-                                                      h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE,
-                                                      h->dNcost, h->q_k, h->dNeedQ);
+        static const int minb = getenv("PGURESVT_EVAL_MINB") ? atoi(getenv("PGURESVT_EVAL_MINB")) : 6;
+        auto kev = (minb >= 8) ? k_eval3<8> : (minb >= 6) ? k_eval3<6> : k_eval3<4>;
+        kev<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds, h->P,
+                                               h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dNcost, h->q_k,
+                                               h->dNeedQ);
         LAUNCHED(h);
         k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->eval_blocks, h->dPartial);
         LAUNCHED(h);
