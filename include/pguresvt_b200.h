@@ -128,7 +128,8 @@ int pguresvt_download(pguresvt_handle *h, double *Y_full, double *estimates_full
  *  [11] bytes of SVD factors resident per frame   [12]/[13] mean Jacobi sweeps (object 0 / warm-started objects)
  *  [14]/[15] ARPS frame pairs computed / reused from the cross-window cache
  *  [16] singular triplets streamed by all evaluations   [17] ms search preparation (weights, multipliers, q-forms)
- *  [18] evaluations redone because a triplet beyond the lazily prepared q-forms survived */
+ *  [18] evaluations redone because a triplet beyond the lazily prepared q-forms survived
+ *  [19] optimiser probes answered from the per-frame memo (a lambda already evaluated bit for bit) */
 #define PGS_NSTATS 24
 int pguresvt_get_stats(const pguresvt_handle *h, double *stats);
 

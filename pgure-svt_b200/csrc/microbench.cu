@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(128) k_tma_patch(const __grid_constant__ CUten
     if (g < reps)
     {
         const int k = g;
-        const int yy = min(max(y + ((int)(patch * 7 + k) % 5) - 2, 0), M1 - 1);
+        // NB the box start must be 16-byte aligned in the innermost dimension: odd FP64 rows raise "illegal instruction"
+        // (measured), so this variant only visits even rows; arbitrary rows would need 6-row boxes padded with zeros.
+        const int yy = min(max(y + ((int)(patch * 7 + k) % 5) - 2, 0), M1 - 1) & ~1;
         const unsigned sa = (unsigned)__cvta_generic_to_shared(&sbox[grp][k][0]);
         if (MODE == 2)
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(yy),

@@ -1036,12 +1036,24 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
         double last = start;
         int err = PGS_OK;
         // NB the PGURE object receives (alpha, sigma, mu) for its (alpha, mu, sigma) — SURVEY Q1
+        // The 1-D subplex search re-probes points it has already visited (restarts re-evaluate the best vertex, shrink
+        // steps land on earlier reflections): ~20 % of a frame's probes repeat an earlier lambda bit for bit.  The
+        // reference's objective is deterministic, so a repeat returns the identical value there; serving repeats from
+        // a per-frame memo reproduces exactly that (and saves the device pass).
+        std::vector<std::pair<double, double>> memo;
         auto f = [&](double x) -> double {
             double v = 0;
-            last = x;
+            last = x; // PGURE::lambda is overwritten by every probe, repeated or not (pgure.hpp:128)
+            for (const auto &m : memo)
+                if (m.first == x)
+                {
+                    h->stats[19] += 1;
+                    return m.second;
+                }
             const int e = objective(h, x, alpha, sigma, mu, &v, nullptr);
             if (e && !err)
                 err = e;
+            memo.emplace_back(x, v);
             return v;
         };
         const int st = opt.minimize(f, start, std::sqrt(start));
