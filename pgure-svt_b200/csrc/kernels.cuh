@@ -633,6 +633,14 @@ __device__ __forceinline__ double load_perturbed(const double *__restrict__ u, s
     return v;
 }
 
+// window of a perturbed SVT object, U + eps*delta (pgure.hpp:80-82), written out once per object so that the register
+// SVD kernel gathers plain doubles (same expression as load_perturbed, hence bit-identical to perturbing on the fly)
+__global__ void k_perturb_window(const double *__restrict__ u, Perturb pt, size_t n, double *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = load_perturbed(u, i, pt);
+}
+
 __device__ __forceinline__ void jacobi_cs(double A, double B, double G, double tol2, double &c, double &s, bool &rot)
 {
     c = 1.0;
@@ -1097,7 +1105,7 @@ __device__ __forceinline__ void cp_async_wait()
 
 template <int WARM, int TRACK>
 __global__ void __launch_bounds__(128, 2)
-    k_svd16_l4(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
+    k_svd16_l4(const double *__restrict__ u, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
                int vecSize, int N, double *__restrict__ fac, const double *__restrict__ fac0, int max_sweeps, double tol2,
                double big2, int *__restrict__ sweeps_out)
 {
@@ -1133,7 +1141,7 @@ __global__ void __launch_bounds__(128, 2)
         const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * k;
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            a[r][k + 1] = load_perturbed(u, vox + r, pt);
+            a[r][k + 1] = __ldg(u + vox + r);
     }
 #pragma unroll
     for (int r = 0; r < 4; r++)
@@ -1379,7 +1387,7 @@ __global__ void __launch_bounds__(128, 2)
                 double ao[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++)
-                    ao[r] = load_perturbed(u, vox + r, pt);
+                    ao[r] = __ldg(u + vox + r);
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {

@@ -77,7 +77,7 @@ struct pguresvt_handle
     // device
     void *dX = nullptr;
     uint16_t *dZ = nullptr, *dTmp16 = nullptr;
-    double *dU = nullptr, *dW = nullptr;
+    double *dU = nullptr, *dW = nullptr, *dUp = nullptr; // dUp: window of the perturbed object being decomposed
     short2 *dPos = nullptr, *dArpsF = nullptr, *dArpsB = nullptr;
     struct ArpsTag
     {
@@ -158,7 +158,7 @@ static void free_all(pguresvt_handle *h)
         if (p)
             cudaFree(p);
     };
-    F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
+    F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dUp), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
@@ -301,6 +301,8 @@ static int create_impl(pguresvt_handle *h)
     }
     if (p.optimize_pgure)
     {
+        if (h->use_l4)
+            CU(cudaMalloc(&h->dUp, wtot * sizeof(double)));
         CU(cudaMalloc(&h->dD1, wtot));
         CU(cudaMalloc(&h->dD2, wtot));
     }
@@ -699,9 +701,17 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         const int variant = h->p.svd_kernel == 3 ? 0 : 1;
         auto cold = variant == 1 ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
         auto warm = variant == 1 ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
+        const double *usrc = h->dU;
+        if (obj != 0)
+        { // U + eps*delta written out once (pgure.hpp:80-82); the SVD kernel then gathers plain doubles
+            const size_t wtot = h->fsz * h->win;
+            k_perturb_window<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dU, pt, wtot, h->dUp);
+            LAUNCHED(h);
+            usrc = h->dUp;
+        }
         if (obj == 0)
-            cold<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
-                                                         max_sweeps, tol2, big2, h->dSweeps);
+            cold<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr, max_sweeps,
+                                                         tol2, big2, h->dSweeps);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
         {
             const int smem_warm = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
@@ -710,8 +720,8 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
                 CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
                 h->attr_warm = true;
             }
-            warm<<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
-                                                         h->dFac[0], max_sweeps, tol2, big2, h->dSweeps);
+            warm<<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], h->dFac[0],
+                                                                 max_sweeps, tol2, big2, h->dSweeps);
         }
     }
     else if (h->use_reg_svd)
