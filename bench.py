@@ -282,11 +282,21 @@ def main():
     flops_per_launch = 77400.0 * (svds / svd_launches) if svd_launches else 0.0
     svd_ms_per_launch = stage_ms["ms_svd"] / svd_launches if svd_launches else 0.0
     achieved_tf = flops_per_launch / (svd_ms_per_launch * 1e-3) / 1e12 if svd_ms_per_launch > 0 else 0.0
-    roofline = {"kernel": "k_svd16_l4 (4-lane register Jacobi, 16x15)", "bound": "fp64", "achieved": achieved_tf, "peak": fp64,
-                "unit": "TFLOP/s", "frac": achieved_tf / fp64 if fp64 else None, "traffic": None,
+    traffic, traffic2 = None, None
+    try:  # per-launch DRAM bytes of the same kernels from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
+        if size == 1024:
+            traffic = tj["k_svd16_l4"]["per_launch_avg_bytes"] if nobj == 3 else tj["k_svd16_l4"]["cold_bytes"]
+            traffic2 = tj["k_eval3"]["bytes"]
+    except Exception:
+        pass
+    roofline = {"kernel": "k_svd16_l4 (4-lane register Jacobi, 16x15, tracked pair norms)", "bound": "fp64", "achieved": achieved_tf,
+                "peak": fp64, "unit": "TFLOP/s", "frac": achieved_tf / fp64 if fp64 else None, "traffic": traffic,
                 "peak_source": fp64_src, "note": "FP64 vector-pipe bound (tensor cores not applicable); algorithmic "
-                "flops 14mn^2+8n^3 = 77,400 per SVD x SVDs per launch / CUDA-event time of the SVD stage per launch; ncu "
-                "(profiles/) shows the FP64 pipe 59% busy on the cold kernel: one-sided Jacobi executes ~3.6x the algorithmic flops",
+                "flops 14mn^2+8n^3 = 77,400 per SVD x SVDs per launch / CUDA-event time of the SVD stage per launch (events on the "
+                "handle's own stream); ncu (profiles/r01) shows the FP64 pipe 53-59% busy: one-sided Jacobi executes ~2.3x the "
+                "algorithmic flops; traffic = DRAM bytes per launch from the committed ncu capture (the kernel is not HBM-bound: "
+                "~6 GB per 8 ms launch)",
                 "share_of_step": stage_ms["ms_svd"] / stage_ms["ms_total"] if stage_ms["ms_total"] else None}
     # secondary: one lambda-search evaluation (k_eval3 + k_risk_uhat).  Algorithmic bytes per evaluation: S and q of the
     # three objects (768 B per patch) + the surviving singular triplets of object 0 (256 B each) + the 240-entry block
@@ -298,9 +308,11 @@ def main():
     alg_bytes = (evals * (npatch * (768 + 1920) + size * size * 15 * 20) + trip * 256) / evals if evals else 0.0
     ach_gbs = alg_bytes / (search_ms_per_eval * 1e-3) / 1e9 if search_ms_per_eval > 0 else 0.0
     roofline2 = {"kernel": "k_eval3 + k_risk_uhat (one PGURE evaluation)", "bound": "hbm", "achieved": ach_gbs, "peak": hbm,
-                 "unit": "GB/s", "frac": ach_gbs / hbm if hbm else None, "traffic": None, "peak_source": hbm_src,
+                 "unit": "GB/s", "frac": ach_gbs / hbm if hbm else None, "traffic": traffic2, "peak_source": hbm_src,
                  "note": "algorithmic bytes = S+q of 3 objects + surviving triplets of object 0 + RED block + voxel pass; "
-                 "ncu: L2 (LTS) is the busiest unit (FP64 RED sector-ops), not DRAM",
+                 "ncu: L2 (LTS) is the busiest unit (FP64 RED sector-ops), not DRAM; the overlap-add pattern alone (microbench) "
+                 "runs at 450 G RED/s = 0.55 ms per evaluation, the kernel takes 0.79 ms",
+                 "probes_per_frame": (evals + acc.get("evals_memoized", 0.0) / n) / fps_step if fps_step else None,
                  "evals_per_frame": ev_per_frame, "algorithmic_bytes_per_eval": alg_bytes,
                  "triplets_per_patch_per_eval": trip / (evals * npatch) if evals else None}
     line = {"metric": "denoised frames/s (1024^2, PGURE lambda)" if not args.fixed_lambda else "denoised frames/s (fixed lambda)",
@@ -312,6 +324,8 @@ def main():
             "gpu_launches": int(round(launches * args.steps)),
             "patch_svds_per_s": svds * world * args.steps / dt,
             "patch_svds_per_s_kernel": (svds / (stage_ms["ms_svd"] * 1e-3)) if stage_ms["ms_svd"] else None,
+            "timing": "wall clock between device synchronisations over K steps (the host-driven lambda search is part of the step), "
+                      "max over ranks; per-stage times are CUDA events on the handle's stream",
             "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_secondary": roofline2,
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline and world == 1:

@@ -479,6 +479,7 @@ def test_cli_config1_example_tif(tmp_path):
     (dict(trajectory_length=7, patch_size=5, patch_overlap=3), 40, 9),   # skewed patch set with uncovered pixels (Q5, Q17)
     (dict(trajectory_length=15, motion_window=3, motion_filter=1), 48, 16),  # small search window, 3x3 median, non-2^N frame
     (dict(trajectory_length=9, patch_size=8, patch_overlap=4), 64, 11),   # 64x9 Casorati matrices
+    (dict(trajectory_length=31, patch_size=8), 40, 33),        # BASELINE configs[4] shape: 64x31 Casorati matrices, ARPS on
 ])
 def test_edge_case_configurations_fixed_lambda(kw, N, F):
     X, _ = synthetic_sequence(N, F, seed=N + F)
@@ -501,6 +502,45 @@ def test_edge_case_pgure_small_windows():
     rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
     assert rel.max() < LAM_TOL, rel
     assert per_frame_rel_err(s.Y_, ref) < 1e-4
+
+
+def test_config5_shape_pgure_small():
+    """BASELINE configs[4] shape at a size the oracle finishes in seconds: patch 8, trajectory 31 (64x31 Casorati
+    matrices), PGURE lambda search, ARPS on — generic shared-memory SVD + unfused evaluation kernels."""
+    X, _ = synthetic_sequence(32, 33, seed=5)
+    args = dict(trajectory_length=31, patch_size=8, optimize_pgure=True, lambda1=-1.0, noise_alpha=0.1, noise_mu=0.05,
+                noise_sigma=0.05, random_seed=1)  # interior optimum (lambda ~ 36.9) rather than the upper bound
+    t = 16
+    h = bridge.Handle(X, frame_begin=t, frame_end=t + 1, **args)
+    h.process()
+    Yh, eh = h.download()
+    h.close()
+    ref, est = orc.pguresvt(X, frame_begin=t, frame_end=t + 1, **args)
+    assert abs(eh[t, 0] - est[t, 0]) / abs(est[t, 0]) < LAM_TOL
+    assert np.abs(Yh[:, :, t] - ref[:, :, t]).max() / np.abs(ref[:, :, t]).max() < 1e-4
+
+
+def test_full_size_properties_1024_pgure():
+    """BASELINE configs[3] frame size (1024^2, patch 4, trajectory 15, PGURE): the oracle cannot run this size, so the
+    production path (4-lane register SVD + fused three-object evaluation with q-forms) is checked against the
+    independent generic path (shared-memory SVD + per-object reconstruction + five-sum risk kernel), which the small
+    tests pin to the oracle: same objective values, same per-frame lambda and pixels within the parity tolerances."""
+    X, _ = synthetic_sequence(1024, 15, seed=11)
+    kw = dict(optimize_pgure=True, lambda1=-1.0, noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03, random_seed=1,
+              frame_begin=7, frame_end=8)
+    lams = [0.0, 0.05, 0.3, 2.0]
+    out = {}
+    for k in (0, 1):
+        h = bridge.Handle(X, svd_kernel=k, **kw)
+        vals, _ = h.probe_pgure(7, 0.05, 0.03, 0.03, lams)
+        h.process()
+        Y, e = h.download()
+        out[k] = (vals, Y[:, :, 7].copy(), e[7, 0], h.stats())
+        h.close()
+    assert out[0][3]["svds"] == 3 * 1021 * 1021
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-9 * np.abs(out[1][0]).max()
+    assert abs(out[0][2] - out[1][2]) / abs(out[1][2]) < LAM_TOL
+    assert np.abs(out[0][1] - out[1][1]).max() / np.abs(out[1][1]).max() < 1e-4
 
 
 def test_too_short_sequence_and_bad_arguments_are_errors_not_crashes():
