@@ -1544,7 +1544,7 @@ __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
-            double *__restrict__ acc0, double *__restrict__ partial, unsigned long long *__restrict__ ktot, int qmax,
+            double *__restrict__ acc0, double *__restrict__ partial, int *__restrict__ kpart, int qmax,
             int *__restrict__ need_more_q)
 {
     // One PGURE evaluation for 16 x 15 patches and the three SVT objects U, U +- eps2*delta2.  16 lanes per patch; lane g
@@ -1597,7 +1597,7 @@ __global__ void __launch_bounds__(128, MINB)
     };
     request_chunk(0, 0);
     cp_async_commit();
-    const int id = ids[pidx];
+    const int id = ids ? ids[pidx] : pidx; // ids == nullptr: the patch set is the full macroblock grid (patch_overlap 1)
     const int r = g & 3, c = g >> 2;
     const int fsz = N * N;
     int vox[SVD16_N];
@@ -1667,90 +1667,60 @@ __global__ void __launch_bounds__(128, MINB)
     }
     else
         s4 = 0.0;
+    // per-warp partials (no CTA barrier): partial[4 * blockIdx.x + warp] = s4 part, kpart[...] = triplets fetched
     s4 = warp_sum(s4);
-    __shared__ double sm4[4];
-    __shared__ int smk[4];
     if (lane == 0)
     {
-        sm4[threadIdx.x >> 5] = s4;
-        smk[threadIdx.x >> 5] = 2 * Kw; // triplets of object 0 fetched for the warp's two patches (upper bound per patch)
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        partial[blockIdx.x] = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
-        atomicAdd(ktot, (unsigned long long)(smk[0] + smk[1] + smk[2] + smk[3]));
+        const int w = 4 * blockIdx.x + (threadIdx.x >> 5);
+        partial[w] = s4;
+        kpart[w] = 2 * Kw; // triplets of object 0 fetched for the warp's two patches (upper bound per patch)
     }
 }
 
 // voxel pass of the fused evaluation: Uhat = acc0 / weights (non-finite -> 0, svt.hpp:163-164);
 // s1 = sum (Uhat - U)^2, s5 = sum Uhat; the accumulator is cleared on the way for the next evaluation, and the
 // per-CTA s4 partials of k_eval3 are folded in (third sum) so that one fixed-order reduction finishes all three.
-// partial: gridDim.x * 3 doubles
-__global__ void k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
-                            const double *__restrict__ s4part, int ns4, double *__restrict__ partial)
+// partial: gridDim.x * 4 doubles (s1, s5, s4, triplets streamed)
+__global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
+                            const double *__restrict__ s4part, const int *__restrict__ kpart, int ns4, double *__restrict__ partial)
 {
-    double s1 = 0, s5 = 0, s4 = 0;
-    { // four independent voxels per step so that twelve loads are in flight per thread; the quotient acc / weights is
-      // formed as a * rcp(c) with one residual correction (no division subroutine in the loop)
-        const size_t stride = (size_t)gridDim.x * blockDim.x;
-        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        for (; i + 3 * stride < tot; i += 4 * stride)
-        {
-            double a[4], uu[4];
-            unsigned c[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-            {
-                a[j] = acc0[i + j * stride];
-                c[j] = cnt[i + j * stride];
-                uu[j] = u[i + j * stride];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-            {
-                acc0[i + j * stride] = 0.0;
-                const double cd = (double)c[j];
-                const double r = __drcp_rn(cd);
-                double q = a[j] * r;
-                q = fma(r, fma(-cd, q, a[j]), q);
-                const double v0 = isfinite(q) ? q : 0.0;
-                const double d = v0 - uu[j];
-                s1 = fma(d, d, s1);
-                s5 += v0;
-            }
-        }
-        for (; i < tot; i += stride)
-        {
-            const double v0 = norm_or_zero(acc0[i], cnt[i]);
-            acc0[i] = 0.0;
-            const double d = v0 - u[i];
-            s1 = fma(d, d, s1);
-            s5 += v0;
-        }
+    double s1 = 0, s5 = 0, s4 = 0, sk = 0;
+    // (an unrolled variant with more loads in flight per thread needs 58 registers, halves the resident CTAs and is slower)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const double v0 = norm_or_zero(acc0[i], cnt[i]);
+        acc0[i] = 0.0;
+        const double d = v0 - u[i];
+        s1 = fma(d, d, s1);
+        s5 += v0;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns4; i += gridDim.x * blockDim.x)
+    {
         s4 += s4part[i];
-    __shared__ double sm[3][32];
+        sk += (double)kpart[i];
+    }
+    __shared__ double sm[4][32];
     s1 = warp_sum(s1);
     s5 = warp_sum(s5);
     s4 = warp_sum(s4);
+    sk = warp_sum(sk);
     if ((threadIdx.x & 31) == 0)
     {
         sm[0][threadIdx.x >> 5] = s1;
         sm[1][threadIdx.x >> 5] = s5;
         sm[2][threadIdx.x >> 5] = s4;
+        sm[3][threadIdx.x >> 5] = sk;
     }
     __syncthreads();
     if (threadIdx.x < 32)
     {
 #pragma unroll
-        for (int q = 0; q < 3; q++)
+        for (int q = 0; q < 4; q++)
         {
             double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
             r = warp_sum(r);
             if (threadIdx.x == 0)
-                partial[(size_t)blockIdx.x * 3 + q] = r;
+                partial[(size_t)blockIdx.x * 4 + q] = r;
         }
     }
 }

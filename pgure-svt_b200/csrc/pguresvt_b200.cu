@@ -114,6 +114,7 @@ struct pguresvt_handle
     bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false, acc0_clean = false;
     int q_k = 0;           // number of leading triplets whose q-forms exist for the current frame
     int *dNeedQ = nullptr; // set by k_eval3 when a triplet beyond q_k survives
+    int *dKpart = nullptr; // per-warp count of singular triplets streamed by k_eval3
     long long cur_t = -1;
     double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
@@ -161,7 +162,7 @@ static void free_all(pguresvt_handle *h)
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dUp), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
-    F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
+    F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
     if (h->noise_thread.joinable())
         h->noise_thread.join();
@@ -312,7 +313,8 @@ static int create_impl(pguresvt_handle *h)
         if (wtot >= ((size_t)1 << 31))
             return fail(PGS_ERR_UNSUPPORTED, "window of %zu voxels exceeds the fused evaluation kernel's 32-bit indexing", wtot);
         CU(cudaMalloc(&h->dC4, wtot * sizeof(double)));
-        CU(cudaMalloc(&h->dPartialE, (size_t)h->eval_blocks * sizeof(double)));
+        CU(cudaMalloc(&h->dPartialE, (size_t)4 * h->eval_blocks * sizeof(double)));
+        CU(cudaMalloc(&h->dKpart, (size_t)4 * h->eval_blocks * sizeof(int)));
 
         for (int k = 0; k < 3; k++)
             CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
@@ -320,7 +322,7 @@ static int create_impl(pguresvt_handle *h)
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
     CU(cudaMemset(h->dOut, 0, 16 * sizeof(double)));
-    h->dNeedQ = reinterpret_cast<int *>(h->dOut + 3); // travels home with the three sums of objective_fused
+    h->dNeedQ = reinterpret_cast<int *>(h->dOut + 4); // travels home with the four sums of objective_fused
     CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
     CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
@@ -764,7 +766,7 @@ static int launch_qform(pguresvt_handle *h, int kmax)
                                                    h->dQ[0], h->dQ[1], h->dQ[2], kmax);
     LAUNCHED(h);
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st)); // dOut[3] is shared with the five-sum objective
+    CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st)); // dOut[4] is shared with the five-sum objective
     h->q_k = kmax;
     return PGS_OK;
 }
@@ -824,17 +826,19 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     {
         static const int minb = getenv("PGURESVT_EVAL_MINB") ? atoi(getenv("PGURESVT_EVAL_MINB")) : 6;
         auto kev = (minb >= 8) ? k_eval3<8> : (minb >= 6) ? k_eval3<6> : k_eval3<4>;
-        kev<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos, h->dIds, h->P,
-                                               h->vecSize, h->N, lambda, h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dNcost, h->q_k,
-                                               h->dNeedQ);
+        kev<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos,
+                                               h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
+                                               h->dAcc[0], h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
         LAUNCHED(h);
-        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->eval_blocks, h->dPartial);
+        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, 4 * h->eval_blocks,
+                                                    h->dPartial);
         LAUNCHED(h);
-        k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 3, h->dOut);
+        k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
         LAUNCHED(h);
-        CU(cudaMemcpyAsync(h->hOut, h->dOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(h->hOut, h->dOut, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
-        if (!*reinterpret_cast<const int *>(h->hOut + 3))
+        h->stats[16] += h->hOut[3]; // singular triplets streamed by this pass (algorithmic-bytes accounting for bench.py)
+        if (!*reinterpret_cast<const int *>(h->hOut + 4))
             break;
         // a triplet beyond the lazily prepared q-forms survived at this lambda: prepare all of them and redo the pass
         int rc = launch_qform(h, SVD16_N);
@@ -1073,13 +1077,6 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
             return fail(PGS_ERR_OPT,
                         "lambda search cannot start from %g (zero initial step; the reference's NLopt call throws here)", start);
         lambda = last; // the LAST evaluated lambda, not the optimum (pgure.hpp:128,236)
-        if (h->use_fused_eval)
-        { // singular triplets streamed by the evaluations of this frame (algorithmic-bytes accounting for bench.py)
-            unsigned long long kt = 0;
-            CU(cudaMemcpyAsync(&kt, h->dNcost, sizeof(kt), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
-            h->stats[16] += (double)kt;
-        }
     }
     {
         StageTimer tm(h, 7);
