@@ -1678,6 +1678,39 @@ __global__ void __launch_bounds__(128, MINB)
     }
 }
 
+// Final reconstruction of ONE slice (the only one the driver consumes, pguresvt.hpp:155-166) for 16 x 15 patches in the
+// l4 record format: 16 lanes per patch, lane g owns block row g; the thresholded spectrum is sorted, so only the
+// surviving leading triplets are read (S: 128 B, then 136 B per survivor instead of the whole 3,968-byte record).
+__global__ void __launch_bounds__(128)
+    k_final16(const double *__restrict__ fac0, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
+              double lambda, int expw, int kref, double *__restrict__ acc)
+{
+    const int lane = threadIdx.x & 31, g = threadIdx.x & 15;
+    int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const double *R = fac0 + (size_t)SVD16_REC * pidx;
+    const double *S = R + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+    const double f = (g < SVD16_N) ? soft_f(S[g], S[15], lambda, expw) : 0.0;
+    unsigned m = __ballot_sync(0xffffffffu, f != 0.0);
+    m = (m | (m >> 16)) & 0xffffu;
+    const int Kw = 32 - __clz(m); // one past the largest surviving index over both patches of the warp
+    double a = 0.0;
+    for (int kk = 0; kk < Kw; kk++)
+    {
+        const double fk = __shfl_sync(0xffffffffu, f, (lane & 16) | kk);
+        if (fk != 0.0)
+            a = fma(R[SVD16_M * kk + g] * fk, R[SVD16_M * SVD16_N + SVD16_LDV * kk + kref], a);
+    }
+    if (valid)
+    {
+        const int id = ids ? ids[pidx] : pidx;
+        const short2 p = pos[(size_t)kref * vecSize + id];
+        atomicAdd(acc + (size_t)(p.x + (g & 3)) + (size_t)N * (p.y + (g >> 2)) + (size_t)N * N * kref, a);
+    }
+}
+
 // voxel pass of the fused evaluation: Uhat = acc0 / weights (non-finite -> 0, svt.hpp:163-164);
 // s1 = sum (Uhat - U)^2, s5 = sum Uhat; the accumulator is cleared on the way for the next evaluation, and the
 // per-CTA s4 partials of k_eval3 are folded in (third sum) so that one fixed-order reduction finishes all three.

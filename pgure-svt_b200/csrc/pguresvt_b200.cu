@@ -753,7 +753,7 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
     return PGS_OK;
 }
 
-#define QFORM_LAZY_K 4
+#define QFORM_LAZY_K 2
 static int launch_qform(pguresvt_handle *h, int kmax)
 {
     const int smem = 8 * 3 * 480 * (int)sizeof(double);
@@ -795,6 +795,14 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
         CU(cudaMemsetAsync(h->dAcc[obj] + h->fsz * only_k, 0, h->fsz * sizeof(double), h->st));
     else
         CU(cudaMemsetAsync(h->dAcc[obj], 0, wtot * sizeof(double), h->st));
+    if (h->use_l4 && obj == 0 && only_k >= 0)
+    { // output slice of the register-SVD configuration: rank-adaptive single-slice kernel
+        k_final16<<<cdiv((long long)h->P * 16, 128), 128, 0, h->st>>>(h->dFac[0], h->dPos, h->P == h->vecSize ? nullptr : h->dIds, h->P,
+                                                                      h->vecSize, h->N, lambda, h->p.exp_weighting, only_k, h->dAcc[0]);
+        LAUNCHED(h);
+        CU(cudaGetLastError());
+        return PGS_OK;
+    }
     const int G = (h->m <= 16) ? 16 : 32;
     const int threads = 128, gpb = threads / G;
     const int NMAX = (h->n <= 16) ? 16 : 32;
