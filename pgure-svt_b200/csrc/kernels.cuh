@@ -1540,7 +1540,16 @@ __global__ void __launch_bounds__(128, 2)
     }
 }
 
-template <int MINB>
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+#define EV_STAGE 144 /* doubles per prefetch stage: S,q of 3 objects (96) | leading triplet U,V (32) | 15 positions (16 ints) | pad */
+#define EV_GRP2 (2 * EV_STAGE + 2 * EV_CH)
+
+template <int MINB, int PPG>
 __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
@@ -1554,127 +1563,174 @@ __global__ void __launch_bounds__(128, MINB)
     //  * Uhat enters the risk non-linearly, so object 0's block is rebuilt (rank-adaptively: singular values are sorted
     //    and the soft threshold is monotone, so the survivors are a prefix) and overlap-added with fire-and-forget
     //    FP64 REDs — per slice the 16 lanes cover the patch's 4 x 4 footprint.
-    // Factor data is streamed through shared memory with 16-byte cp.async copies: S and q of the three objects and
-    // the first EV_C triplets of object 0 are requested before anything depends on them, further chunks are
-    // double-buffered behind the arithmetic.
-    __shared__ __align__(16) double smem[8 * EV_GRP];
+    // A CTA covers 8 * PPG consecutive patches; each 16-lane group walks PPG of them and prefetches the next patch's
+    // S, q, leading triplet and trajectory with cp.async (two stages) while the REDs of the current one are issued.
+    // Triplets beyond the leading one (rare) are fetched on demand in chunks of EV_C, double-buffered.
+    __shared__ __align__(16) double smem[8 * EV_GRP2];
     const int lane = threadIdx.x & 31;
     const int g = threadIdx.x & 15;
-    double *sg = smem + (threadIdx.x >> 4) * EV_GRP;
-    int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const bool valid = pidx < P;
-    if (!valid)
-        pidx = P - 1;
-    const size_t roff = (size_t)SVD16_REC * pidx;
-    const double *R0 = fac0 + roff;
+    const int grp = threadIdx.x >> 4;
+    double *sg = smem + grp * EV_GRP2;
     const int soff = SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
-    if (g < 8)
-    { // S of the three objects
-        cp_async16(sg + 0 + 2 * g, fac0 + roff + soff + 2 * g);
-        cp_async16(sg + 16 + 2 * g, fac2 + roff + soff + 2 * g);
-        cp_async16(sg + 32 + 2 * g, fac3 + roff + soff + 2 * g);
-    }
-    else
-    { // q of the three objects
-        const int h2 = 2 * (g - 8);
-        cp_async16(sg + 48 + h2, q0 + (size_t)16 * pidx + h2);
-        cp_async16(sg + 64 + h2, q2 + (size_t)16 * pidx + h2);
-        cp_async16(sg + 80 + h2, q3 + (size_t)16 * pidx + h2);
-    }
-    // chunk 0 is the leading triplet alone (on typical data it is the only survivor), later chunks hold EV_C triplets
-    auto request_chunk = [&](int c0, int buf) {
-        double *dst = sg + 96 + buf * EV_CH;
-#pragma unroll
-        for (int c = 0; c < EV_C; c++)
-        {
-            const int kk = c0 + c;
-            if (kk < SVD16_N && (c0 > 0 || c == 0))
-            {
-                // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
-                const double *src = (g < 8) ? R0 + SVD16_M * kk + 2 * g : R0 + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
-                cp_async16(dst + c * 32 + 2 * g, src);
-            }
-        }
-    };
-    request_chunk(0, 0);
-    cp_async_commit();
-    const int id = ids ? ids[pidx] : pidx; // ids == nullptr: the patch set is the full macroblock grid (patch_overlap 1)
     const int r = g & 3, c = g >> 2;
     const int fsz = N * N;
-    int vox[SVD16_N];
-#pragma unroll
-    for (int k = 0; k < SVD16_N; k++)
-    {
-        const short2 p = pos[(size_t)k * vecSize + id];
-        vox[k] = (p.x + r) + N * (p.y + c) + fsz * k;
-    }
-    cp_async_wait<0>();
-    __syncwarp();
-    double f0 = 0.0, s4 = 0.0;
-    if (g < SVD16_N)
-    {
-        f0 = soft_f(sg[g], sg[15], lambda, expw);
-        const double f2 = soft_f(sg[16 + g], sg[16 + 15], lambda, expw);
-        const double f3 = soft_f(sg[32 + g], sg[32 + 15], lambda, expw);
-        s4 = fma(f2, sg[64 + g], fma(f3, sg[80 + g], -2.0 * f0 * sg[48 + g]));
-        // q-forms are prepared lazily for the leading qmax triplets only; a survivor beyond them invalidates this pass
-        if (g >= qmax && (f0 != 0.0 || f2 != 0.0 || f3 != 0.0) && valid)
-            *need_more_q = 1;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, f0 != 0.0);
-    m = (m | (m >> 16)) & 0xffffu;
-    const int Kw = 32 - __clz(m); // one past the largest surviving index over both patches of the warp (0 if none)
-    double a0[SVD16_N];
-#pragma unroll
-    for (int k = 0; k < SVD16_N; k++)
-        a0[k] = 0.0;
-    int buf = 0;
-    for (int c0 = 0; c0 < Kw; c0 += (c0 ? EV_C : 1))
-    {
-        const int nxt = c0 ? c0 + EV_C : 1;
-        if (nxt < Kw)
-            request_chunk(nxt, buf ^ 1);
-        cp_async_commit();
-        const double *cb = sg + 96 + buf * EV_CH;
-#pragma unroll
-        for (int cc = 0; cc < EV_C; cc++)
-        {
-            const int kk = c0 + cc;
-            if (kk < Kw && (c0 > 0 || cc == 0))
-            {
-                const double fk0 = __shfl_sync(0xffffffffu, f0, (lane & 16) | kk);
-                const double *b0 = cb + cc * 32;
-                const double u0 = b0[g] * fk0;
-                const double2 *v0 = reinterpret_cast<const double2 *>(b0 + 16);
-#pragma unroll
-                for (int k2 = 0; k2 < 8; k2++)
-                {
-                    const double2 x0 = v0[k2];
-                    a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
-                    if (2 * k2 + 1 < SVD16_N)
-                        a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
-                }
-            }
+    const int base = blockIdx.x * (8 * PPG) + grp;
+
+    auto issue = [&](int j, int st) {
+        int pidx = base + 8 * j;
+        if (pidx >= P)
+            pidx = P - 1;
+        const size_t roff = (size_t)SVD16_REC * pidx;
+        double *dst = sg + st * EV_STAGE;
+        if (g < 8)
+        { // S of the three objects, U column 0
+            cp_async16(dst + 0 + 2 * g, fac0 + roff + soff + 2 * g);
+            cp_async16(dst + 16 + 2 * g, fac2 + roff + soff + 2 * g);
+            cp_async16(dst + 32 + 2 * g, fac3 + roff + soff + 2 * g);
+            cp_async16(dst + 96 + 2 * g, fac0 + roff + 2 * g);
         }
-        cp_async_wait<0>();
-        __syncwarp();
-        buf ^= 1;
-    }
-    if (valid)
+        else
+        { // q of the three objects, V column 0
+            const int h2 = 2 * (g - 8);
+            cp_async16(dst + 48 + h2, q0 + (size_t)16 * pidx + h2);
+            cp_async16(dst + 64 + h2, q2 + (size_t)16 * pidx + h2);
+            cp_async16(dst + 80 + h2, q3 + (size_t)16 * pidx + h2);
+            cp_async16(dst + 112 + h2, fac0 + roff + SVD16_M * SVD16_N + h2);
+        }
+        if (g < SVD16_N)
+        { // trajectory position of slice g
+            const int id = ids ? ids[pidx] : pidx; // ids == nullptr: the patch set is the full macroblock grid (patch_overlap 1)
+            cp_async4(reinterpret_cast<int *>(dst + 128) + g, pos + (size_t)g * vecSize + id);
+        }
+        cp_async_commit();
+    };
+
+    double s4tot = 0.0;
+    int ktot = 0;
+    issue(0, 0);
+#pragma unroll 1
+    for (int j = 0; j < PPG; j++)
     {
+        const int st = j & 1;
+        if (j + 1 < PPG)
+            issue(j + 1, st ^ 1);
+        else
+            cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        int pidx = base + 8 * j;
+        const bool valid = pidx < P;
+        if (!valid)
+            pidx = P - 1;
+        const double *R0 = fac0 + (size_t)SVD16_REC * pidx;
+        const double *ss = sg + st * EV_STAGE;
+        const short2 *sp = reinterpret_cast<const short2 *>(ss + 128);
+        double f0 = 0.0, s4 = 0.0;
+        if (g < SVD16_N)
+        {
+            f0 = soft_f(ss[g], ss[15], lambda, expw);
+            const double f2 = soft_f(ss[16 + g], ss[16 + 15], lambda, expw);
+            const double f3 = soft_f(ss[32 + g], ss[32 + 15], lambda, expw);
+            s4 = fma(f2, ss[64 + g], fma(f3, ss[80 + g], -2.0 * f0 * ss[48 + g]));
+            // q-forms are prepared lazily for the leading qmax triplets only; a survivor beyond them invalidates this pass
+            if (g >= qmax && (f0 != 0.0 || f2 != 0.0 || f3 != 0.0) && valid)
+                *need_more_q = 1;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, f0 != 0.0);
+        m = (m | (m >> 16)) & 0xffffu;
+        const int Kw = 32 - __clz(m); // one past the largest surviving index over both patches of the warp (0 if none)
+        double a0[SVD16_N];
 #pragma unroll
         for (int k = 0; k < SVD16_N; k++)
-            atomicAdd(acc0 + vox[k], a0[k]);
+            a0[k] = 0.0;
+        if (Kw > 0)
+        { // leading triplet from the prefetch stage
+            const double fk0 = __shfl_sync(0xffffffffu, f0, lane & 16);
+            const double u0 = ss[96 + g] * fk0;
+            const double2 *v0 = reinterpret_cast<const double2 *>(ss + 112);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++)
+            {
+                const double2 x0 = v0[k2];
+                a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
+                if (2 * k2 + 1 < SVD16_N)
+                    a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
+            }
+        }
+        if (Kw > 1)
+        { // further survivors: chunks of EV_C triplets, double-buffered (waits also drain the prefetch of the next patch)
+            double *cbuf = sg + 2 * EV_STAGE;
+            auto request_chunk = [&](int c0, int buf) {
+                double *dst = cbuf + buf * EV_CH;
+#pragma unroll
+                for (int cc = 0; cc < EV_C; cc++)
+                {
+                    const int kk = c0 + cc;
+                    if (kk < SVD16_N)
+                    {
+                        // lanes 0..7: U column kk (16 doubles), lanes 8..15: V column kk
+                        const double *src = (g < 8) ? R0 + SVD16_M * kk + 2 * g : R0 + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
+                        cp_async16(dst + cc * 32 + 2 * g, src);
+                    }
+                }
+            };
+            int buf = 0;
+            request_chunk(1, 0);
+            cp_async_commit();
+            for (int c0 = 1; c0 < Kw; c0 += EV_C)
+            {
+                if (c0 + EV_C < Kw)
+                    request_chunk(c0 + EV_C, buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const double *cb = cbuf + buf * EV_CH;
+#pragma unroll
+                for (int cc = 0; cc < EV_C; cc++)
+                {
+                    const int kk = c0 + cc;
+                    if (kk < Kw)
+                    {
+                        const double fk0 = __shfl_sync(0xffffffffu, f0, (lane & 16) | kk);
+                        const double *b0 = cb + cc * 32;
+                        const double u0 = b0[g] * fk0;
+                        const double2 *v0 = reinterpret_cast<const double2 *>(b0 + 16);
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; k2++)
+                        {
+                            const double2 x0 = v0[k2];
+                            a0[2 * k2] = fma(u0, x0.x, a0[2 * k2]);
+                            if (2 * k2 + 1 < SVD16_N)
+                                a0[2 * k2 + 1] = fma(u0, x0.y, a0[2 * k2 + 1]);
+                        }
+                    }
+                }
+                __syncwarp();
+                buf ^= 1;
+            }
+            cp_async_wait<0>();
+        }
+        if (valid)
+        {
+#pragma unroll
+            for (int k = 0; k < SVD16_N; k++)
+            {
+                const short2 p = sp[k];
+                atomicAdd(acc0 + ((p.x + r) + N * (p.y + c) + fsz * k), a0[k]);
+            }
+            s4tot += s4;
+        }
+        ktot += 2 * Kw; // triplets of object 0 fetched for the warp's two patches (upper bound per patch)
+        __syncwarp(); // the stage is overwritten by the prefetch issued in the next iteration
     }
-    else
-        s4 = 0.0;
+    cp_async_wait<0>();
     // per-warp partials (no CTA barrier): partial[4 * blockIdx.x + warp] = s4 part, kpart[...] = triplets fetched
-    s4 = warp_sum(s4);
+    s4tot = warp_sum(s4tot);
     if (lane == 0)
     {
         const int w = 4 * blockIdx.x + (threadIdx.x >> 5);
-        partial[w] = s4;
-        kpart[w] = 2 * Kw; // triplets of object 0 fetched for the warp's two patches (upper bound per patch)
+        partial[w] = s4tot;
+        kpart[w] = ktot;
     }
 }
 

@@ -123,6 +123,7 @@ struct pguresvt_handle
 };
 
 #define RISK_BLOCKS 1184
+#define EVAL_PPG 8 /* patches each 16-lane group of k_eval3 walks (software-pipelined) */
 #define LAUNCHED(h) ((h)->launches++)
 
 static size_t dtype_size(int dt) { return dt == PGS_U8 ? 1 : dt == PGS_U16 ? 2 : dt == PGS_F32 ? 4 : 8; }
@@ -832,13 +833,14 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     }
     for (int attempt = 0; attempt < 2; attempt++)
     {
-        static const int minb = getenv("PGURESVT_EVAL_MINB") ? atoi(getenv("PGURESVT_EVAL_MINB")) : 6;
-        auto kev = (minb >= 8) ? k_eval3<8> : (minb >= 6) ? k_eval3<6> : k_eval3<4>;
-        kev<<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos,
-                                               h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
-                                               h->dAcc[0], h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
+        static const int ppg = getenv("PGURESVT_EVAL_PPG") ? atoi(getenv("PGURESVT_EVAL_PPG")) : EVAL_PPG;
+        auto kev = (ppg == 1) ? k_eval3<6, 1> : (ppg == 4) ? k_eval3<6, 4> : (ppg == 16) ? k_eval3<6, 16> : (ppg == 32) ? k_eval3<6, 32> : k_eval3<6, 8>;
+        const int ppg_eff = (ppg == 1 || ppg == 4 || ppg == 16 || ppg == 32) ? ppg : 8;
+        kev<<<cdiv(h->P, 8 * ppg_eff), 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos,
+                                                        h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
+                                                        h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
         LAUNCHED(h);
-        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, 4 * h->eval_blocks,
+        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, 4 * cdiv(h->P, 8 * ppg_eff),
                                                     h->dPartial);
         LAUNCHED(h);
         k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
