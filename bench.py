@@ -313,8 +313,8 @@ def main():
     roofline2 = {"kernel": "k_eval3 + k_risk_uhat (one PGURE evaluation)", "bound": "hbm", "achieved": ach_gbs, "peak": hbm,
                  "unit": "GB/s", "frac": ach_gbs / hbm if hbm else None, "traffic": traffic2, "peak_source": hbm_src,
                  "note": "algorithmic bytes = S+q of 3 objects + surviving triplets of object 0 + RED block + voxel pass; "
-                 "ncu: L2 (LTS) is the busiest unit (FP64 RED sector-ops), not DRAM; the overlap-add pattern alone (microbench) "
-                 "runs at 450 G RED/s = 0.55 ms per evaluation, the kernel takes 0.79 ms",
+                 "ncu (profiles/r01): k_eval3 0.56 ms with L2 (LTS) at 78% — 111 M FP64 RED sectors per evaluation at ~200 G sectors/s, "
+                 "the L2 atomic ceiling the overlap-add pattern reaches on its own (microbench: 450 G RED/s); DRAM 1.4 GB per evaluation",
                  "probes_per_frame": (evals + acc.get("evals_memoized", 0.0) / n) / fps_step if fps_step else None,
                  "evals_per_frame": ev_per_frame, "algorithmic_bytes_per_eval": alg_bytes,
                  "triplets_per_patch_per_eval": trip / (evals * npatch) if evals else None}

@@ -1066,7 +1066,10 @@ static int noise_analyse_batch(NoiseWorkspace &ws, const double *dU, int N, cons
         const int *a3 = dBig;
         double *a5 = ws.dScratch, *a6 = ws.dLeaf;
         void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
-        static const int big_div = getenv("PGURESVT_BIG_GRID_DIV") ? atoi(getenv("PGURESVT_BIG_GRID_DIV")) : 4;
+        // steady state (one new slice per frame): a quarter of the SMs, like the line fit; a cold window (many whole-frame
+        // regions back to back) is throughput-bound and takes the whole grid
+        static const int big_div_env = getenv("PGURESVT_BIG_GRID_DIV") ? atoi(getenv("PGURESVT_BIG_GRID_DIV")) : 0;
+        const int big_div = big_div_env > 0 ? big_div_env : (lbig.size() > 4 ? 1 : 4);
         NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(std::max(1, ws.grid / big_div)), dim3(512), args, 0, st));
         if (launches)
             (*launches)++;
