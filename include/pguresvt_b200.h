@@ -43,7 +43,7 @@ typedef struct pguresvt_params
     int32_t device;            /* CUDA device ordinal */
     int32_t eps1_mode;         /* 0: as the reference computes it (eps1*delta1 integer-truncated to 0,
                                   pgure.hpp:80); 1: intended first-order perturbation */
-    int32_t svd_kernel;        /* 0: auto; 1: generic shared-memory Jacobi; 2: 8-lane register Jacobi; 3: 4-lane register Jacobi without norm tracking */
+    int32_t svd_kernel;        /* 0: auto (4-lane register Jacobi, tracked norms, fast scaled rotations); 1: generic shared-memory Jacobi; 2: 8-lane register Jacobi; 3: 4-lane without norm tracking; 4: 4-lane tracked norms, full rotations */
     int32_t reserved;
 } pguresvt_params;
 

@@ -1048,6 +1048,43 @@ __device__ __forceinline__ void jacobi_cs_track(double &A, double &B, double G, 
     B -= w;
 }
 
+// Fast (scaled) rotation for a slot pair: the columns are kept UNNORMALISED, true column = scale * stored column, so that
+// applying  x' = c (x - t y),  y' = c (y + t x)  costs two FMAs per element pair,
+//     x_st' = x_st - alpha y_st,   y_st' = y_st + beta x_st,   alpha = t sy / sx,  beta = t sx / sy,
+// with the factor c absorbed into the two scales (and 1/c into their tracked reciprocals).  A, B: tracked TRUE squared norms;
+// G: inner product of the STORED columns.  c >= 1/sqrt(2), so over the at most 30 x 16 rotations of a column the scales stay
+// within 2^-240 .. 1 — no renormalisation is needed.
+__device__ __forceinline__ void jacobi_fast_givens(double &A, double &B, double &sx, double &sy, double &isx, double &isy, double G,
+                                                   double tol2, double big2, double &alpha, double &beta, bool &big)
+{
+    const double Gt = G * (sx * sy);
+    const double g2 = Gt * Gt, ab = A * B;
+    const bool rot = g2 > tol2 * ab;
+    big = big || (g2 > big2 * ab);
+    const double d = B - A;
+    const double q = fma(d, d, 4.0 * g2);
+    double rq, rd;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rq) : "d"(q));
+    const double den = fma(q, rq, fabs(d)); // |d| + sqrt(d^2 + 4 G^2)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
+    const double G2 = Gt + Gt;
+    const double t = rot ? ((d >= 0.0) ? G2 : -G2) * rd : 0.0;
+    const double x1 = fma(t, t, 1.0);
+    const double cc = rsqrt_fast(x1);
+    const double c = rot ? cc : 1.0;
+    const double h = rot ? x1 * cc : 1.0; // 1 / c
+    const double s = c * t;
+    const double w = s * fma(s, d, -c * G2);
+    A += w;
+    B -= w;
+    alpha = t * (sy * isx);
+    beta = t * (sx * isy);
+    sx *= c;
+    sy *= c;
+    isx *= h;
+    isy *= h;
+}
+
 // transposing reduction of 8 values over the 4 lanes of a group: lane `sub` gets the sums of x[2*sub], x[2*sub+1]
 __device__ __forceinline__ void tr4_8(const double (&x)[8], int sub, double &o0, double &o1)
 {
@@ -1180,6 +1217,7 @@ __global__ void __launch_bounds__(128, 2)
 
     int sweep = 0;
     double nr[4] = {0.0, 0.0, 0.0, 0.0}; // TRACK: squared norms of slots 4*sub .. 4*sub+3
+    double sc[4] = {1.0, 1.0, 1.0, 1.0}, isc[4] = {1.0, 1.0, 1.0, 1.0}; // TRACK == 2: column scales of those slots and reciprocals
 #pragma unroll 1
     for (; sweep < max_sweeps;)
     {
@@ -1198,6 +1236,12 @@ __global__ void __launch_bounds__(128, 2)
                 n2s[j] = sacc;
             }
             tr4_16(n2s, sub, nr);
+            if (TRACK == 2)
+            {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    nr[j] *= sc[j] * sc[j];
+            }
         }
 #pragma unroll 2
         for (int round = 0; round < 16; round++) // 16 rounds = the 15-round cycle plus its first pair set again: an even count lets
@@ -1219,16 +1263,34 @@ __global__ void __launch_bounds__(128, 2)
                 }
                 double G0, G1;
                 tr4_8(pg, sub, G0, G1);
-                jacobi_cs_track(nr[0], nr[1], G0, tol2, big2, c0, s0, big);
-                jacobi_cs_track(nr[2], nr[3], G1, tol2, big2, c1, s1, big);
+                if (TRACK == 2)
+                { // c0/s0, c1/s1 carry (alpha, beta) of the two pairs
+                    jacobi_fast_givens(nr[0], nr[1], sc[0], sc[1], isc[0], isc[1], G0, tol2, big2, c0, s0, big);
+                    jacobi_fast_givens(nr[2], nr[3], sc[2], sc[3], isc[2], isc[3], G1, tol2, big2, c1, s1, big);
+                }
+                else
+                {
+                    jacobi_cs_track(nr[0], nr[1], G0, tol2, big2, c0, s0, big);
+                    jacobi_cs_track(nr[2], nr[3], G1, tol2, big2, c1, s1, big);
+                }
                 // the norms travel with their columns (RR_MOVE below): slot 4s <- 4s-2, 4s+2 <- 4s, 4s+1 <- 4s+3, 4s+3 <- 4s+5
-                const double up = __shfl_up_sync(0xffffffffu, nr[2], 1, 4);
-                const double dn = __shfl_down_sync(0xffffffffu, nr[1], 1, 4);
-                const double o0 = nr[0], o1 = nr[1], o2 = nr[2], o3 = nr[3];
-                nr[0] = (sub == 0) ? 0.0 : up;
-                nr[1] = o3;
-                nr[2] = (sub == 0) ? o1 : o0;
-                nr[3] = (sub == 3) ? o2 : dn;
+#define SLOT_STATE_MOVE(X, PAD)                                      \
+    {                                                                \
+        const double up = __shfl_up_sync(0xffffffffu, X[2], 1, 4);   \
+        const double dn = __shfl_down_sync(0xffffffffu, X[1], 1, 4); \
+        const double o0 = X[0], o1 = X[1], o2 = X[2], o3 = X[3];     \
+        X[0] = (sub == 0) ? PAD : up;                                \
+        X[1] = o3;                                                   \
+        X[2] = (sub == 0) ? o1 : o0;                                 \
+        X[3] = (sub == 3) ? o2 : dn;                                 \
+    }
+                SLOT_STATE_MOVE(nr, 0.0)
+                if (TRACK == 2)
+                {
+                    SLOT_STATE_MOVE(sc, 1.0)
+                    SLOT_STATE_MOVE(isc, 1.0)
+                }
+#undef SLOT_STATE_MOVE
             }
             else
             {
@@ -1266,8 +1328,16 @@ __global__ void __launch_bounds__(128, 2)
                 for (int r = 0; r < 4; r++)
                 {
                     const double x = a[r][2 * i], y = a[r][2 * i + 1];
-                    a[r][2 * i] = fma(ci, x, -si * y);
-                    a[r][2 * i + 1] = fma(si, x, ci * y);
+                    if (TRACK == 2)
+                    { // (ci, si) = (alpha, beta) of the fast rotation
+                        a[r][2 * i] = fma(-ci, y, x);
+                        a[r][2 * i + 1] = fma(si, x, y);
+                    }
+                    else
+                    {
+                        a[r][2 * i] = fma(ci, x, -si * y);
+                        a[r][2 * i + 1] = fma(si, x, ci * y);
+                    }
                 }
             }
 #define RR_MOVE(X)                 \
@@ -1301,6 +1371,17 @@ __global__ void __launch_bounds__(128, 2)
             break;
     }
 
+    if (TRACK == 2)
+    { // true columns = scale * stored columns; the scale of slot j sits in lane j >> 2
+#pragma unroll
+        for (int j = 1; j < 16; j++)
+        {
+            const double sj = __shfl_sync(0xffffffffu, sc[j & 3], j >> 2, 4);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                a[r][j] *= sj;
+        }
+    }
     // squared column norms: lane `sub` gets columns 4*sub .. 4*sub+3, then everybody gets all 16 sigmas
     double n2[16], q[4];
 #pragma unroll
@@ -1361,72 +1442,62 @@ __global__ void __launch_bounds__(128, 2)
     }
     if (valid && sub == 3)
         R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 15] = smax; // slot 15 carries sigma_max
-    // ranks of the four columns this lane ends up with in the V rebuild (k = 4*sub + kl)
-    int rkm[4];
+    // V(i, k) = sum_rows A(row, i) * z(row, k).  z is handed over through shared memory (the V0 buffer of the warm start is
+    // dead by now; the cold kernel is launched with the same allocation): lane `sub` then owns rows i = 4*sub .. 4*sub+3 of V,
+    // re-gathers those four complete columns of A (16 values each) and forms all 15 inner products per column locally —
+    // no cross-lane reduction (the shuffle/select tree this replaces cost as much as seven Jacobi rounds).
+    double *zs = sv0 + (size_t)(threadIdx.x >> 2) * SVD16_V0_STRIDE; // z(row, k) at zs[16 * k + row]
+    __syncwarp();
 #pragma unroll
-    for (int kl = 0; kl < 4; kl++)
+    for (int k = 0; k < SVD16_N; k++)
     {
-        const int r0 = rk[kl], r1 = rk[4 + kl], r2 = rk[8 + kl], r3 = (12 + kl < SVD16_N) ? rk[(12 + kl < SVD16_N) ? 12 + kl : 0] : 0;
-        rkm[kl] = (sub == 0) ? r0 : (sub == 1) ? r1 : (sub == 2) ? r2 : r3;
+        double2 *dst = reinterpret_cast<double2 *>(zs + 16 * k + 4 * sub);
+        dst[0] = make_double2(a[0][k + 1], a[1][k + 1]);
+        dst[1] = make_double2(a[2][k + 1], a[3][k + 1]);
     }
-    // V(i, k) = sum_rows A(row, i) * z(row, k): loop over i, reduce over the 4 lanes, lane `sub` keeps k = 4*sub..4*sub+3;
-    // four consecutive i are buffered so that each store is 4 contiguous doubles of one column of V
+    double ac[4][16]; // [column 4*sub + ii of A][row]
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+    {
+        const int i = min(4 * sub + ii, SVD16_N - 1); // (lane 3's fourth column is the zero padding row of V: value unused)
+        const short2 p = pos[(size_t)i * vecSize + id];
+        const size_t vox = (size_t)p.x + (size_t)N * p.y + fsz * i;
+#pragma unroll
+        for (int c2 = 0; c2 < 4; c2++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                ac[ii][4 * c2 + r] = __ldg(u + vox + (size_t)N * c2 + r);
+    }
+    __syncwarp();
     double *Vg = R + SVD16_M * SVD16_N;
 #pragma unroll
-    for (int i0 = 0; i0 < 16; i0 += 4)
+    for (int k = 0; k < SVD16_N; k++)
     {
-        double vb[4][4]; // [k local][i local]
+        double zk[16];
+#pragma unroll
+        for (int h2 = 0; h2 < 8; h2++)
+        {
+            const double2 v = reinterpret_cast<const double2 *>(zs + 16 * k)[h2];
+            zk[2 * h2] = v.x;
+            zk[2 * h2 + 1] = v.y;
+        }
+        double vo[4];
 #pragma unroll
         for (int ii = 0; ii < 4; ii++)
         {
-            const int i = i0 + ii;
-            double part[16];
-            if (i < SVD16_N)
-            {
-                const short2 p = pos[(size_t)i * vecSize + id];
-                const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * i;
-                double ao[4];
+            double sacc = 0.0;
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    ao[r] = __ldg(u + vox + r);
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                {
-                    double sacc = 0.0;
-                    if (k < SVD16_N)
-                    {
-#pragma unroll
-                        for (int r = 0; r < 4; r++)
-                            sacc = fma(ao[r], a[r][k + 1], sacc);
-                    }
-                    part[k] = sacc;
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                    part[k] = 0.0;
-            }
-            double o[4];
-            tr4_16(part, sub, o);
-#pragma unroll
-            for (int kl = 0; kl < 4; kl++)
-                vb[kl][ii] = o[kl];
+            for (int row = 0; row < 16; row++)
+                sacc = fma(ac[ii][row], zk[row], sacc);
+            vo[ii] = sacc;
         }
+        if (sub == 3)
+            vo[3] = 0.0; // row 15 of V is padding
         if (valid)
         {
-#pragma unroll
-            for (int kl = 0; kl < 4; kl++)
-            {
-                const int k = 4 * sub + kl;
-                if (k < SVD16_N)
-                {
-                    double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * rkm[kl] + i0);
-                    dst[0] = make_double2(vb[kl][0], vb[kl][1]);
-                    dst[1] = make_double2(vb[kl][2], vb[kl][3]);
-                }
-            }
+            double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * rk[k] + 4 * sub);
+            dst[0] = make_double2(vo[0], vo[1]);
+            dst[1] = make_double2(vo[2], vo[3]);
         }
     }
     if (sweeps_out && (threadIdx.x & 31) == 0)

@@ -701,9 +701,10 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         // 0: tracked pair norms; 3: legacy variant that recomputes the pair norms every round
         // (unrolling the 15 rounds removes the register moves of the round-robin permutation but the loop then outgrows
         //  the instruction cache: measured 1.15x (3 rounds) to 1.7x (15 rounds) slower on B200)
-        const int variant = h->p.svd_kernel == 3 ? 0 : 1;
-        auto cold = variant == 1 ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
-        auto warm = variant == 1 ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
+        // 4: tracked norms with full rotations; 0 (default): tracked norms with fast (scaled) rotations
+        const int variant = h->p.svd_kernel == 3 ? 0 : h->p.svd_kernel == 4 ? 1 : 2;
+        auto cold = variant == 2 ? k_svd16_l4<0, 2> : variant == 1 ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
+        auto warm = variant == 2 ? k_svd16_l4<1, 2> : variant == 1 ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
         const double *usrc = h->dU;
         if (obj != 0)
         { // U + eps*delta written out once (pgure.hpp:80-82); the SVD kernel then gathers plain doubles
@@ -712,20 +713,20 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
             LAUNCHED(h);
             usrc = h->dUp;
         }
-        if (obj == 0)
-            cold<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr, max_sweeps,
-                                                         tol2, big2, h->dSweeps);
-        else // perturbed objects start from the V of object 0 (computed first for this frame)
-        {
-            const int smem_warm = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
-            if (!h->attr_warm)
-            { // per device: the handle is bound to one device
-                CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warm));
-                h->attr_warm = true;
-            }
-            warm<<<cdiv(nthreads, 128), 128, smem_warm, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], h->dFac[0],
-                                                                 max_sweeps, tol2, big2, h->dSweeps);
+        // dynamic shared memory: V of object 0 for the warm start, re-used for the hand-over of z in the V rebuild (both variants)
+        const int smem_svd = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
+        if (!h->attr_warm)
+        { // per device: the handle is bound to one device
+            CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
+            CU(cudaFuncSetAttribute(cold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
+            h->attr_warm = true;
         }
+        if (obj == 0)
+            cold<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
+                                                                max_sweeps, tol2, big2, h->dSweeps);
+        else // perturbed objects start from the V of object 0 (computed first for this frame)
+            warm<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], h->dFac[0],
+                                                                max_sweeps, tol2, big2, h->dSweeps);
     }
     else if (h->use_reg_svd)
     {

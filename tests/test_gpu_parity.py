@@ -104,7 +104,7 @@ def test_arps_motion_estimation_off_leaves_zero_positions(ref_test_cube):
 
 
 # ------------------------------------------------------------------ SVD / reconstruct / risk
-@pytest.mark.parametrize("svd_kernel", [0, 1, 2, 3])
+@pytest.mark.parametrize("svd_kernel", [0, 1, 2, 3, 4])
 def test_singular_values_vs_lapack(golden, svd_kernel):
     X = golden["X"]
     t, fw = 8, 7
@@ -140,7 +140,7 @@ def test_singular_values_of_perturbed_objects_warm_start(golden, obj):
     h.close()
 
 
-@pytest.mark.parametrize("svd_kernel", [1, 2, 3])
+@pytest.mark.parametrize("svd_kernel", [1, 2, 3, 4])
 def test_pgure_objective_other_svd_kernels(golden, svd_kernel):
     """The generic (shared-memory) and 8-lane register SVD kernels feed the unfused evaluation path."""
     X = golden["X"]
