@@ -1397,26 +1397,33 @@ __global__ void __launch_bounds__(128, 2)
         n2[j] = sacc;
     }
     tr4_16(n2, sub, q);
-    double sig[16];
+    double sig[16], so[4];
+#pragma unroll
+    for (int jl = 0; jl < 4; jl++)
+        so[jl] = sqrt(q[jl]); // sigma of the lane's own columns 4*sub .. 4*sub+3
 #pragma unroll
     for (int j = 0; j < 16; j++)
-        sig[j] = __shfl_sync(0xffffffffu, sqrt(q[j & 3]), j >> 2, 4);
+        sig[j] = __shfl_sync(0xffffffffu, so[j & 3], j >> 2, 4);
     double smax = 0.0;
 #pragma unroll
     for (int j = 0; j < SVD16_N; j++)
         smax = fmax(smax, sig[j]);
 
-    // descending order like LAPACK (svt.hpp:111): rank of every column, computed redundantly by every lane
-    int rk[SVD16_N];
+    // descending order like LAPACK (svt.hpp:111): every lane ranks its own four columns, then the ranks are exchanged
+    int rk[SVD16_N], rko[4];
 #pragma unroll
-    for (int j = 0; j < SVD16_N; j++)
+    for (int jl = 0; jl < 4; jl++)
     {
+        const int j = 4 * sub + jl;
         int rr = 0;
 #pragma unroll
         for (int t2 = 0; t2 < SVD16_N; t2++)
-            rr += (sig[t2] > sig[j] || (sig[t2] == sig[j] && t2 < j)) ? 1 : 0;
-        rk[j] = rr;
+            rr += (sig[t2] > so[jl] || (sig[t2] == so[jl] && t2 < j)) ? 1 : 0;
+        rko[jl] = rr;
     }
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+        rk[j] = __shfl_sync(0xffffffffu, rko[j & 3], j >> 2, 4);
     double *R = fac + (size_t)SVD16_REC * pidx;
     // U = W / sigma (columns with sigma below 1e-20 sigma_max carry nothing after thresholding: set to zero);
     // afterwards a[r][j+1] holds z = w / sigma^2 for the V rebuild
