@@ -1627,6 +1627,76 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 #define EV_STAGE 144 /* doubles per prefetch stage: S,q of 3 objects (96) | leading triplet U,V (32) | 15 positions (16 ints) | pad */
 #define EV_GRP2 (2 * EV_STAGE + 2 * EV_CH)
 
+// K_qform for the leading KQ triplets only (the lazy default): same arithmetic as k_qform3 with a compact staging buffer
+// (3 x KQ x 32 doubles per patch instead of the whole U and V of three objects), which lifts the residency from 2 to 8 CTAs
+// per SM — the kernel is bound by the latency of the C4 gather.
+template <int KQ>
+__global__ void __launch_bounds__(128, 8)
+    k_qform3_lead(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
+                  const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, const double *__restrict__ c4,
+                  double *__restrict__ q0, double *__restrict__ q2, double *__restrict__ q3)
+{
+    __shared__ __align__(16) double sq[8 * 3 * KQ * 32];
+    const int g = threadIdx.x & 15;
+    double *sg = sq + (size_t)(threadIdx.x >> 4) * (3 * KQ * 32);
+    int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const size_t roff = (size_t)SVD16_REC * pidx;
+    const double *R[3] = {fac0 + roff, fac2 + roff, fac3 + roff};
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+#pragma unroll
+        for (int kk = 0; kk < KQ; kk++)
+        { // lanes 0..7: U column kk, lanes 8..15: V column kk
+            const double *src = (g < 8) ? R[o] + SVD16_M * kk + 2 * g : R[o] + SVD16_M * SVD16_N + SVD16_LDV * kk + 2 * (g - 8);
+            cp_async16(sg + (o * KQ + kk) * 32 + 2 * g, src);
+        }
+    cp_async_commit();
+    const int id = ids ? ids[pidx] : pidx;
+    const int r = g & 3, c = g >> 2;
+    const int fsz = N * N;
+    double cw[SVD16_N];
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        cw[k] = c4[(p.x + r) + N * (p.y + c) + fsz * k];
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    double *qd[3] = {q0, q2, q3};
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+    {
+        double mine = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KQ; kk++)
+        {
+            const double *b = sg + (o * KQ + kk) * 32;
+            const double2 *v = reinterpret_cast<const double2 *>(b + 16);
+            double z = 0.0;
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++)
+            {
+                const double2 x = v[k2];
+                z = fma(cw[2 * k2], x.x, z);
+                if (2 * k2 + 1 < SVD16_N)
+                    z = fma(cw[2 * k2 + 1], x.y, z);
+            }
+            double val = b[g] * z;
+#pragma unroll
+            for (int sh = 8; sh > 0; sh >>= 1)
+                val += __shfl_xor_sync(0xffffffffu, val, sh);
+            if (g == kk)
+                mine = val;
+        }
+        if (valid)
+            qd[o][(size_t)16 * pidx + g] = mine; // slots >= KQ are written as 0 and flagged by k_eval3 if ever needed
+    }
+}
+
 template <int MINB, int PPG>
 __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,

@@ -758,14 +758,21 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
 #define QFORM_LAZY_K 2
 static int launch_qform(pguresvt_handle *h, int kmax)
 {
-    const int smem = 8 * 3 * 480 * (int)sizeof(double);
-    if (!h->attr_qform)
+    if (kmax == QFORM_LAZY_K)
+        k_qform3_lead<QFORM_LAZY_K><<<h->eval_blocks, 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos,
+                                                                       h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N,
+                                                                       h->dC4, h->dQ[0], h->dQ[1], h->dQ[2]);
+    else
     {
-        CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        h->attr_qform = true;
+        const int smem = 8 * 3 * 480 * (int)sizeof(double);
+        if (!h->attr_qform)
+        {
+            CU(cudaFuncSetAttribute(k_qform3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            h->attr_qform = true;
+        }
+        k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dC4,
+                                                       h->dQ[0], h->dQ[1], h->dQ[2], kmax);
     }
-    k_qform3<<<h->eval_blocks, 128, smem, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dC4,
-                                                   h->dQ[0], h->dQ[1], h->dQ[2], kmax);
     LAUNCHED(h);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st)); // dOut[4] is shared with the five-sum objective
