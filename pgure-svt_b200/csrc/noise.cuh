@@ -554,6 +554,7 @@ __device__ void grid_select2(Get get, int n, int kA, int kB, double &outA, doubl
                     {
                         spre[2 * which] = prefix | ((unsigned long long)(lane * 8 + q) << shift);
                         spre[2 * which + 1] = (unsigned long long)(kk - before);
+                        spre[4 + which] = (unsigned long long)loc[q]; // population of the chosen bin
                     }
                     before += loc[q];
                 }
@@ -564,8 +565,30 @@ __device__ void grid_select2(Get get, int n, int kA, int kB, double &outA, doubl
         ka = (int)spre[1];
         pB = spre[2];
         kb = (int)spre[3];
+        const bool single = (spre[4] == 1ull && spre[5] == 1ull);
         __syncthreads();
         hslot++;
+        if (single && pass < 7)
+        { // both targets are alone in their bins (typical after 4-5 passes on continuous data): one fetch pass reads their
+          // remaining bits instead of up to four more histogram passes.  The decision is uniform over the grid.
+            unsigned long long *K = reinterpret_cast<unsigned long long *>(gs.ghist + 4 * 512) + 2 * (hslot & 3u);
+            for (int e0 = blockIdx.x * NT; e0 < n; e0 += stride)
+            {
+                const int e = e0 + threadIdx.x;
+                if (e < n)
+                {
+                    const unsigned long long key = key_of(get(e));
+                    if ((key >> shift) == (pA >> shift))
+                        K[0] = key;
+                    if ((key >> shift) == (pB >> shift))
+                        K[1] = key;
+                }
+            }
+            grid.sync();
+            pA = __ldcg(K);
+            pB = __ldcg(K + 1);
+            break;
+        }
     }
     outA = val_of(pA);
     outB = val_of(pB);
@@ -580,7 +603,7 @@ __global__ void __launch_bounds__(NT) k_noise_big(const double *__restrict__ u, 
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[NT / 32];
     __shared__ unsigned hist[512];
-    __shared__ unsigned long long spre[4];
+    __shared__ unsigned long long spre[6];
     unsigned slot = 0, hslot = 0;
     const int gstride = gridDim.x * NT;
     for (int bq = 0; bq < nbig; bq++)
@@ -654,7 +677,7 @@ __global__ void __launch_bounds__(NT) k_noise_wls_grid(const double *__restrict_
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[NT / 32];
     __shared__ unsigned hist[512];
-    __shared__ unsigned long long spre[4];
+    __shared__ unsigned long long spre[6];
     unsigned slot = 0, hslot = 0;
     const int gstride = gridDim.x * NT;
     const double tol = 1E-6, eps = 1E-12;
@@ -821,7 +844,7 @@ static int noise_init(NoiseWorkspace &ws, int sm_count, std::string &err)
     NCU(cudaGetDevice(&ws.device));
     NCU(cudaMalloc(&ws.dFit, 8 * sizeof(double)));
     NCU(cudaMalloc(&ws.dPartials, (size_t)4 * 8 * ws.grid * sizeof(double)));
-    NCU(cudaMalloc(&ws.dHist, 4 * 512 * sizeof(unsigned)));
+    NCU(cudaMalloc(&ws.dHist, 4 * 512 * sizeof(unsigned) + 8 * sizeof(unsigned long long))); // + [4][2] fetched keys
     return 0;
 }
 
