@@ -1218,6 +1218,7 @@ __global__ void __launch_bounds__(128, 2)
     int sweep = 0;
     double nr[4] = {0.0, 0.0, 0.0, 0.0}; // TRACK: squared norms of slots 4*sub .. 4*sub+3
     double sc[4] = {1.0, 1.0, 1.0, 1.0}, isc[4] = {1.0, 1.0, 1.0, 1.0}; // TRACK == 2: column scales of those slots and reciprocals
+    int quiet = 0; // consecutive rounds (warp-wide) without a rotation above the `big` threshold
 #pragma unroll 1
     for (; sweep < max_sweeps;)
     {
@@ -1243,9 +1244,13 @@ __global__ void __launch_bounds__(128, 2)
                     nr[j] *= sc[j] * sc[j];
             }
         }
-#pragma unroll 2
-        for (int round = 0; round < 16; round++) // 16 rounds = the 15-round cycle plus its first pair set again: an even count lets
-                                                 // the body be unrolled by 2, which removes the register moves of RR_MOVE (600 instructions per 2 rounds)
+        // 16 rounds = the 15-round cycle plus its first pair set again: an even count lets the body be unrolled by 2, which
+        // removes the register moves of RR_MOVE; the convergence exit is taken between such double rounds only (an exit
+        // inside the unrolled body would bring the moves back)
+#pragma unroll 1
+        for (int rp = 0; rp < 8 && quiet < 15; rp++)
+#pragma unroll
+        for (int half = 0; half < 2; half++)
         {
             double c0, s0, c1, s1;
             if (TRACK)
@@ -1365,9 +1370,17 @@ __global__ void __launch_bounds__(128, 2)
             RR_MOVE(a[2])
             RR_MOVE(a[3])
 #undef RR_MOVE
+            // every pair is visited once in any 15 consecutive rounds: 15 quiet rounds in a row mean that all pairs were below
+            // the threshold when last rotated, i.e. the state "a whole sweep without a big rotation" — reached here at round
+            // granularity instead of at the next sweep boundary
+            {
+                const bool any_big = __any_sync(0xffffffffu, big);
+                quiet = any_big ? 0 : quiet + 1;
+                big = false;
+            }
         }
         sweep++;
-        if (!__any_sync(0xffffffffu, big))
+        if (quiet >= 15)
             break;
     }
 
