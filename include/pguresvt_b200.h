@@ -44,7 +44,11 @@ typedef struct pguresvt_params
     int32_t eps1_mode;         /* 0: as the reference computes it (eps1*delta1 integer-truncated to 0,
                                   pgure.hpp:80); 1: intended first-order perturbation */
     int32_t svd_kernel;        /* 0: auto (4-lane register Jacobi, tracked norms, fast scaled rotations); 1: generic shared-memory Jacobi; 2: 8-lane register Jacobi; 3: 4-lane without norm tracking; 4: 4-lane tracked norms, full rotations */
-    int32_t reserved;
+    int32_t rank_cache;        /* shapes other than 16x15 with optimize_pgure (eps1_mode 0): the factor cache keeps S and the
+                                  q-forms of every singular triplet plus the leading rank_cache triplets of object U
+                                  (DESIGN.md "truncated factor cache"); probes at which more triplets survive are answered
+                                  exactly by re-decomposing those patches.  0: automatic (as many as half of the free HBM holds, up to all);
+                                  < 0: keep the full U, S, V of every patch (svt.hpp:111-116) */
 } pguresvt_params;
 
 enum
@@ -129,7 +133,9 @@ int pguresvt_download(pguresvt_handle *h, double *Y_full, double *estimates_full
  *  [14]/[15] ARPS frame pairs computed / reused from the cross-window cache
  *  [16] singular triplets streamed by all evaluations   [17] ms search preparation (weights, multipliers, q-forms)
  *  [18] evaluations redone because a triplet beyond the lazily prepared q-forms survived
- *  [19] optimiser probes answered from the per-frame memo (a lambda already evaluated bit for bit) */
+ *  [19] optimiser probes answered from the per-frame memo (a lambda already evaluated bit for bit)
+ *  [20] patches re-decomposed because more than rank_cache triplets survived a probe (compact cache; [18] counts those probes)
+ *  [21] leading triplets of object U kept per patch by the compact cache (0: full factor cache) */
 #define PGS_NSTATS 24
 int pguresvt_get_stats(const pguresvt_handle *h, double *stats);
 

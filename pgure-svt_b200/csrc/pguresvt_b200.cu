@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "compact.cuh"
 #include "noise.cuh"
 #include "sbplx1d.hpp"
 
@@ -69,6 +70,10 @@ struct pguresvt_handle
     bool use_reg_svd = false; // any register-resident 16x15 kernel
     bool use_l4 = false;      // 4-lanes-per-matrix kernel (S in slot order, S[15] = sigma_max)
     bool use_fused_eval = false;
+    bool use_warp_svd = false; // 64 x n Casorati matrices: warp-per-matrix register Jacobi (compact.cuh)
+    bool use_compact = false;  // truncated factor cache (S, q-forms, leading Rc triplets of object 0), compact.cuh
+    int Rc = 0;                // leading singular triplets of object 0 kept per patch
+    int evc_warps = 0;         // warps of the k_eval_c grid (one s4 partial each)
     int eval_blocks = 0;
     int sm_count = 148;
     double vP = 0, d2Neg = 0, d2Pos = 0;
@@ -93,6 +98,13 @@ struct pguresvt_handle
     int8_t *dD1 = nullptr, *dD2 = nullptr;
     double *dPartial = nullptr, *dOut = nullptr, *dMaxPartial = nullptr, *dC4 = nullptr, *dPartialE = nullptr, *dQ[3] = {nullptr, nullptr, nullptr};
     double *dY = nullptr, *dEst = nullptr, *dV = nullptr;
+    double *dSc[4] = {nullptr, nullptr, nullptr, nullptr}, *dQc[4] = {nullptr, nullptr, nullptr, nullptr}; // compact cache: S, q per object
+    double *dLead = nullptr;       // compact cache: leading triplets of object 0
+    int *dOvf = nullptr;           // [0] number of patches whose survivors exceed Rc at the current probe, [1..] their macroblock ids
+    double *dFacScratch = nullptr; // full records of one chunk of overflow patches (allocated on first use)
+    int scratch_patches = 0;
+    int *hOvf = nullptr;           // pinned
+    bool attr_svdw = false;
     int *dSweeps = nullptr;
     unsigned long long *dNcost = nullptr;
     NoiseWorkspace noise_ws;
@@ -163,6 +175,11 @@ static void free_all(pguresvt_handle *h)
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dUp), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
+    for (int i = 0; i < 4; i++)
+        F(h->dSc[i]), F(h->dQc[i]);
+    F(h->dLead), F(h->dOvf), F(h->dFacScratch);
+    if (h->hOvf)
+        cudaFreeHost(h->hOvf);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
     if (h->noise_thread.joinable())
@@ -252,6 +269,9 @@ static int create_impl(pguresvt_handle *h)
         return fail(PGS_ERR_UNSUPPORTED, "register SVD kernels only cover 16x15 Casorati matrices");
     h->use_l4 = h->use_reg_svd && p.svd_kernel != 2; // 0 / 3: 4-lane kernel with tracked / recomputed pair norms
     h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
+    h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
+    // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
+    h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
     {
         const double kappa = 1.;
         h->vP = 0.5 + 0.5 * kappa / std::sqrt(kappa * kappa + 4);
@@ -296,8 +316,16 @@ static int create_impl(pguresvt_handle *h)
     for (int k = 0; k < h->nobj; k++)
     {
         const int o = h->objs[k];
-        if (o == 0 || !h->use_fused_eval)
+        if (o == 0 || !(h->use_fused_eval || h->use_compact))
             CU(cudaMalloc(&h->dAcc[o], wtot * sizeof(double)));
+        if (h->use_compact)
+        {
+            CU(cudaMalloc(&h->dSc[o], (size_t)32 * h->P * sizeof(double)));
+            CU(cudaMalloc(&h->dQc[o], (size_t)32 * h->P * sizeof(double)));
+            CU(cudaMemset(h->dSc[o], 0, (size_t)32 * h->P * sizeof(double)));
+            CU(cudaMemset(h->dQc[o], 0, (size_t)32 * h->P * sizeof(double)));
+            continue;
+        }
         CU(cudaMalloc(&h->dFac[o], h->rec * (size_t)h->P * sizeof(double)));
         CU(cudaMemset(h->dFac[o], 0, h->rec * (size_t)h->P * sizeof(double)));
     }
@@ -330,6 +358,28 @@ static int create_impl(pguresvt_handle *h)
     CU(cudaMalloc(&h->dSweeps, 2 * sizeof(int)));
     CU(cudaMalloc(&h->dNcost, sizeof(unsigned long long)));
     CU(cudaMallocHost(&h->hOut, 16 * sizeof(double)));
+    if (h->use_compact)
+    {
+        h->evc_warps = 4 * std::min(cdiv(h->P, 4), h->sm_count * 16);
+        CU(cudaMalloc(&h->dC4, wtot * sizeof(double)));
+        CU(cudaMalloc(&h->dPartialE, (size_t)h->evc_warps * sizeof(double)));
+        CU(cudaMalloc(&h->dKpart, (size_t)h->evc_warps * sizeof(int)));
+        CU(cudaMalloc(&h->dOvf, ((size_t)h->P + 1) * sizeof(int)));
+        CU(cudaMemset(h->dOvf, 0, sizeof(int)));
+        CU(cudaMallocHost(&h->hOvf, sizeof(int)));
+        // the leading-triplet cache is sized last: explicit rank_cache, else as many ranks (up to all n) as half of the
+        // memory still free holds — the other half stays for the overflow scratch, the noise workspace and the caller
+        const size_t per_rank = (size_t)h->P * (h->m + 32) * sizeof(double);
+        int R = p.rank_cache;
+        if (R == 0)
+        {
+            size_t freeb = 0, totb = 0;
+            CU(cudaMemGetInfo(&freeb, &totb));
+            R = (int)std::min<size_t>(EVC_RMAX, (freeb / 2) / per_rank);
+        }
+        h->Rc = std::max(1, std::min(std::min(R, EVC_RMAX), h->n));
+        CU(cudaMalloc(&h->dLead, per_rank * h->Rc));
+    }
     h->xmax.assign(nres, 0.0);
     h->zmax.assign(nres, 0.0);
     h->est.assign((size_t)4 * nblk, 0.0);
@@ -682,6 +732,60 @@ static int stage_motion(pguresvt_handle *h, uint32_t t) // MotionEstimator::Esti
     return PGS_OK;
 }
 
+// SVD of the patches listed in `ids` for shapes other than 16x15: warp-per-matrix register Jacobi for 64 x n, the
+// shared-memory Jacobi otherwise; mode 0 writes full records (o.fac), mode 1 the compact cache (o.S, o.Q, o.lead).
+static int launch_svd_generic(pguresvt_handle *h, const Perturb &pt, const int *ids, int np, const SvdOut &o, int mode)
+{
+    const int max_sweeps = 30;
+    const double tol = 1e-15, tol2 = tol * tol;
+    if (np <= 0)
+        return PGS_OK;
+    if (h->use_warp_svd)
+    {
+        const double big = 1e-6, big2 = big * big;
+        const int smem = 4 * SVDW_WARP_DOUBLES(2) * (int)sizeof(double);
+        if (!h->attr_svdw)
+        {
+            CU(cudaFuncSetAttribute(k_svd_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(k_svd_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            h->attr_svdw = true;
+        }
+        if (mode == 1)
+            k_svd_warp<2, 1><<<cdiv(np, 4), 128, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n, o,
+                                                                 max_sweeps, tol2, big2, h->dSweeps);
+        else
+            k_svd_warp<2, 0><<<cdiv(np, 4), 128, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n, o,
+                                                                 max_sweeps, tol2, big2, h->dSweeps);
+    }
+    else
+    {
+        const size_t per_warp = ((size_t)h->m * h->n + (size_t)h->n * h->n + h->n) * sizeof(double);
+        int wpb = (int)std::min<size_t>(8, (size_t)(96 * 1024) / per_warp);
+        if (wpb < 1)
+            wpb = 1;
+        const size_t smem = per_warp * wpb;
+        if (smem > 200 * 1024)
+            return fail(PGS_ERR_UNSUPPORTED, "Casorati matrix %dx%d too large for the shared-memory SVD kernel", h->m, h->n);
+        if (mode == 1)
+        {
+            if (smem > 48 * 1024)
+                CU(cudaFuncSetAttribute(k_svd_smem_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_svd_smem_c<<<cdiv(np, wpb), wpb * 32, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n, o,
+                                                                    max_sweeps, tol2, h->dSweeps);
+        }
+        else
+        {
+            if (smem > 48 * 1024)
+                CU(cudaFuncSetAttribute(k_svd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_svd_smem<<<cdiv(np, wpb), wpb * 32, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n,
+                                                                  o.ldv, o.fac, o.rec, max_sweeps, tol2, h->dSweeps);
+        }
+    }
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
 static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-118 (+ pgure.hpp:80-82)
 {
     Perturb pt;
@@ -733,6 +837,22 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         const long long nthreads = (long long)h->P * 8;
         k_svd_16x15<<<cdiv(nthreads, 128), 128, 0, h->st>>>(h->dU, pt, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj],
                                                             max_sweeps, tol2, h->dSweeps);
+    }
+    else if (h->use_warp_svd || h->use_compact)
+    {
+        SvdOut o{};
+        if (h->use_compact)
+        {
+            o.S = h->dSc[obj], o.Q = h->dQc[obj], o.c4 = h->dC4;
+            o.lead = (obj == 0) ? h->dLead : nullptr;
+            o.R = (obj == 0) ? h->Rc : 0;
+        }
+        else
+            o.fac = h->dFac[obj], o.rec = h->rec, o.ldv = h->ldv;
+        int rc = launch_svd_generic(h, pt, h->dIds, h->P, o, h->use_compact ? 1 : 0);
+        if (rc)
+            return rc;
+        h->launches--; // counted once below
     }
     else
     {
@@ -795,10 +915,112 @@ static int stage_count(pguresvt_handle *h, int only_k)
     return PGS_OK;
 }
 
+static int launch_recon_generic(pguresvt_handle *h, const double *fac, const int *ids, int np, double lambda, int only_k, double *acc)
+{
+    const int G = (h->m <= 16) ? 16 : 32;
+    const int threads = 128, gpb = threads / G;
+    const int NMAX = (h->n <= 16) ? 16 : 32;
+    const size_t smem = ((size_t)h->ldv * h->n + 2 * NMAX) * sizeof(double) * gpb;
+    if (NMAX == 16)
+        k_recon<16><<<cdiv(np, gpb), threads, smem, h->st>>>(fac, h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos, ids, np, h->vecSize,
+                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, G);
+    else
+        k_recon<32><<<cdiv(np, gpb), threads, smem, h->st>>>(fac, h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos, ids, np, h->vecSize,
+                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, G);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
+// Compact cache: thresholds + s4 partials + overlap-add of object U's block from the leading Rc triplets (k_eval_c).
+// Patches with more than Rc survivors at this lambda are decomposed again (object U only) in chunks into a scratch
+// buffer of full records and reconstructed by k_recon — the result is exact for any lambda.  The accumulator must be
+// clear (whole window, or slice only_k) on entry.
+static int compact_accumulate(pguresvt_handle *h, double lambda, int only_k, int want_s4)
+{
+    CU(cudaMemsetAsync(h->dOvf, 0, sizeof(int), h->st));
+    k_eval_c<<<h->evc_warps / 4, 128, 0, h->st>>>(h->dSc[0], h->dSc[2], h->dSc[3], h->dQc[0], h->dQc[2], h->dQc[3], h->dLead, h->Rc, h->m, h->n,
+                                                   h->p.block_size, h->dPos, h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, only_k,
+                                                   want_s4, h->dAcc[0], h->dPartialE, h->dKpart, h->dOvf);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->hOvf, h->dOvf, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const int novf = *h->hOvf;
+    if (novf == 0)
+        return PGS_OK;
+    h->stats[18] += 1;
+    h->stats[20] += novf;
+    if (!h->dFacScratch)
+    {
+        const size_t budget = (size_t)2 << 30;
+        h->scratch_patches = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->P, budget / (h->rec * sizeof(double))));
+        CU(cudaMalloc(&h->dFacScratch, h->rec * (size_t)h->scratch_patches * sizeof(double)));
+        CU(cudaMemset(h->dFacScratch, 0, h->rec * (size_t)h->scratch_patches * sizeof(double)));
+    }
+    Perturb pt{};
+    pt.d1 = h->dD1, pt.d2neg = h->dD2, pt.mode = 0, pt.eps = 0.0, pt.dNeg = h->d2Neg, pt.dPos = h->d2Pos;
+    SvdOut o{};
+    o.fac = h->dFacScratch, o.rec = h->rec, o.ldv = h->ldv;
+    for (int off = 0; off < novf; off += h->scratch_patches)
+    {
+        const int np = std::min(h->scratch_patches, novf - off);
+        int rc = launch_svd_generic(h, pt, h->dOvf + 1 + off, np, o, 0);
+        if (rc)
+            return rc;
+        h->stats[1] += np;
+        if ((rc = launch_recon_generic(h, h->dFacScratch, h->dOvf + 1 + off, np, lambda, only_k, h->dAcc[0])))
+            return rc;
+    }
+    return PGS_OK;
+}
+
+static int objective_compact(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
+{
+    const size_t wtot = h->fsz * h->win;
+    if (!h->acc0_clean)
+    { // afterwards every evaluation's voxel pass leaves the accumulator cleared
+        CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
+        h->acc0_clean = true;
+    }
+    int rc = compact_accumulate(h, lambda, -1, 1);
+    if (rc)
+        return rc;
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, h->evc_warps, h->dPartial);
+    LAUNCHED(h);
+    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hOut, h->dOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->stats[16] += h->hOut[3];
+    const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
+    const double sigmasq = sigma * sigma;
+    const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
+    const double OoN = 1.0 / ((double)h->N * h->N * h->win);
+    *value = OoN * (s1 - (alpha + mu) * s2 + (2 / eps1 * s3) - (2 * sigmasq * alpha / (eps2 * eps2) * s4) + (2 * mu * s5) + mu) -
+             sigmasq;
+    if (terms)
+    {
+        terms[0] = s1, terms[1] = s2, terms[2] = s3, terms[3] = s4, terms[4] = s5;
+    }
+    h->stats[2] += 1;
+    return PGS_OK;
+}
+
 static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) // SVT::Reconstruct, svt.hpp:121-160
 {
     if (obj == 0)
         h->acc0_clean = false;
+    if (h->use_compact)
+    {
+        if (obj != 0)
+            return fail(PGS_ERR_ARG, "the compact factor cache reconstructs object U only");
+        if (only_k >= 0)
+            CU(cudaMemsetAsync(h->dAcc[0] + h->fsz * only_k, 0, h->fsz * sizeof(double), h->st));
+        else
+            CU(cudaMemsetAsync(h->dAcc[0], 0, h->fsz * h->win * sizeof(double), h->st));
+        return compact_accumulate(h, lambda, only_k, 0);
+    }
     const size_t wtot = h->fsz * h->win;
     if (only_k >= 0)
         CU(cudaMemsetAsync(h->dAcc[obj] + h->fsz * only_k, 0, h->fsz * sizeof(double), h->st));
@@ -812,21 +1034,7 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
         CU(cudaGetLastError());
         return PGS_OK;
     }
-    const int G = (h->m <= 16) ? 16 : 32;
-    const int threads = 128, gpb = threads / G;
-    const int NMAX = (h->n <= 16) ? 16 : 32;
-    const size_t smem = ((size_t)h->ldv * h->n + 2 * NMAX) * sizeof(double) * gpb;
-    if (NMAX == 16)
-        k_recon<16><<<cdiv(h->P, gpb), threads, smem, h->st>>>(h->dFac[obj], h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos,
-                                                                h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
-                                                                only_k, h->dAcc[obj], G);
-    else
-        k_recon<32><<<cdiv(h->P, gpb), threads, smem, h->st>>>(h->dFac[obj], h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos,
-                                                                h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting,
-                                                                only_k, h->dAcc[obj], G);
-    LAUNCHED(h);
-    CU(cudaGetLastError());
-    return PGS_OK;
+    return launch_recon_generic(h, h->dFac[obj], h->dIds, h->P, lambda, only_k, h->dAcc[obj]);
 }
 
 // One evaluation of PGURE::CalculatePGURE (pgure.hpp:120-137).  (alpha, mu, sigma) are the PGURE object's
@@ -882,6 +1090,8 @@ static int objective(pguresvt_handle *h, double lambda, double alpha, double mu,
 {
     if (h->use_fused_eval)
         return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
+    if (h->use_compact)
+        return objective_compact(h, lambda, alpha, mu, sigma, value, terms);
     for (int k = 0; k < h->nobj; k++)
     {
         int rc = launch_recon(h, h->objs[k], lambda, -1);
@@ -973,7 +1183,7 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         StageTimer tm(h, 17);
         if ((rc = stage_count(h, -1)))
             return rc;
-        if (h->use_fused_eval)
+        if (h->use_fused_eval || h->use_compact)
         { // per-voxel multiplier delta2/weights for the q-forms of this frame
             const size_t wtot = h->fsz * h->win;
             k_c4<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dC4);
@@ -1152,7 +1362,9 @@ extern "C" int pguresvt_process(pguresvt_handle *h)
     cudaEventDestroy(e1);
     h->stats[9] = ms;
     h->stats[0] = (double)h->launches;
-    h->stats[11] = (double)(h->rec * (size_t)h->P * sizeof(double) * h->nobj);
+    h->stats[11] = h->use_compact ? (double)((size_t)h->P * sizeof(double) * (64 * (size_t)h->nobj + (size_t)h->Rc * (h->m + 32)))
+                                  : (double)(h->rec * (size_t)h->P * sizeof(double) * h->nobj);
+    h->stats[21] = h->Rc;
     return PGS_OK;
 }
 
@@ -1270,14 +1482,17 @@ extern "C" int pguresvt_probe_arps(pguresvt_handle *h, uint32_t t, int32_t *patc
 extern "C" int pguresvt_probe_singular_values(pguresvt_handle *h, uint32_t t, int obj, double *S, int64_t *n_patches)
 {
     CHECK_T(h, t);
-    if (obj < 0 || obj > 3 || !h->dFac[obj])
+    if (obj < 0 || obj > 3 || !(h->dFac[obj] || h->dSc[obj]))
         return fail(PGS_ERR_ARG, "SVT object %d not present in this configuration", obj);
     int rc = prepare_frame(h, t);
     if (rc)
         return rc;
     if (n_patches)
         *n_patches = h->P;
-    if (S)
+    if (S && h->use_compact)
+        CU(cudaMemcpy2D(S, (size_t)h->n * sizeof(double), h->dSc[obj], 32 * sizeof(double), (size_t)h->n * sizeof(double), h->P,
+                        cudaMemcpyDeviceToHost));
+    else if (S)
     {
         const size_t soff = (size_t)h->m * h->n + (size_t)h->ldv * h->n;
         CU(cudaMemcpy2D(S, (size_t)h->n * sizeof(double), h->dFac[obj] + soff, h->rec * sizeof(double), (size_t)h->n * sizeof(double),

@@ -39,14 +39,15 @@ class Params(C.Structure):
         ("device", C.c_int32),
         ("eps1_mode", C.c_int32),
         ("svd_kernel", C.c_int32),
-        ("reserved", C.c_int32),
+        ("rank_cache", C.c_int32),
     ]
 
 
 DTYPES = {np.dtype("uint8"): 0, np.dtype("uint16"): 1, np.dtype("float32"): 2, np.dtype("float64"): 3}
 NSTATS = 24
 STAT_NAMES = ["launches", "svds", "evals", "ms_median", "ms_arps", "ms_svd", "ms_search", "ms_final", "ms_noise",
-              "ms_total", "svd_sweeps", "factor_bytes", "sweeps_obj0", "sweeps_warm", "arps_pairs_computed", "arps_pairs_reused", "eval_triplets", "ms_search_prep", "eval_redone", "evals_memoized"]
+              "ms_total", "svd_sweeps", "factor_bytes", "sweeps_obj0", "sweeps_warm", "arps_pairs_computed", "arps_pairs_reused", "eval_triplets", "ms_search_prep", "eval_redone", "evals_memoized",
+              "overflow_patches", "rank_cache"]
 
 
 def lib_path():
@@ -112,17 +113,19 @@ def check(rc, what="pguresvt"):
 def make_params(trajectory_length=15, patch_size=4, patch_overlap=1, motion_window=7, motion_filter=5, noise_method=4,
                 max_iter=500, n_jobs=-1, random_seed=-1, optimize_pgure=True, exponential_weighting=True,
                 motion_estimation=True, lambda1=0.0, noise_alpha=-1.0, noise_mu=-1.0, noise_sigma=-1.0, tol=1e-7,
-                device=None, eps1_mode=None, svd_kernel=None):
+                device=None, eps1_mode=None, svd_kernel=None, rank_cache=None):
     if device is None:
         device = int(os.environ.get("PGURESVT_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     if eps1_mode is None:
         eps1_mode = int(os.environ.get("PGURESVT_EPS1_MODE", "0"))
     if svd_kernel is None:
         svd_kernel = int(os.environ.get("PGURESVT_SVD_KERNEL", "0"))
+    if rank_cache is None:
+        rank_cache = int(os.environ.get("PGURESVT_RANK_CACHE", "0"))
     return Params(int(trajectory_length), int(patch_size), int(patch_overlap), int(motion_window), int(motion_filter),
                   int(noise_method), int(max_iter), int(n_jobs), int(random_seed), int(bool(optimize_pgure)),
                   int(bool(exponential_weighting)), int(bool(motion_estimation)), float(lambda1), float(noise_alpha),
-                  float(noise_mu), float(noise_sigma), float(tol), int(device), int(eps1_mode), int(svd_kernel), 0)
+                  float(noise_mu), float(noise_sigma), float(tol), int(device), int(eps1_mode), int(svd_kernel), int(rank_cache))
 
 
 def _run(entry, dtype, input_images, **kw):

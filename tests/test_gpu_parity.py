@@ -146,7 +146,7 @@ def test_pgure_objective_other_svd_kernels(golden, svd_kernel):
     X = golden["X"]
     alpha, mu, sigma = golden["pgure_params"]
     h = bridge.Handle(X, optimize_pgure=True, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1,
-                      svd_kernel=svd_kernel)
+                      svd_kernel=svd_kernel, rank_cache=-1)
     vals, terms = h.probe_pgure(8, alpha, mu, sigma, golden["pgure_lambdas"])
     assert np.abs(vals - golden["pgure_values"]).max() <= 1e-9 * np.abs(golden["pgure_values"]).max()
     h.close()
@@ -504,20 +504,95 @@ def test_edge_case_pgure_small_windows():
     assert per_frame_rel_err(s.Y_, ref) < 1e-4
 
 
-def test_config5_shape_pgure_small():
+@pytest.mark.parametrize("rank_cache", [0, 1, -1])
+def test_config5_shape_pgure_small(rank_cache):
     """BASELINE configs[4] shape at a size the oracle finishes in seconds: patch 8, trajectory 31 (64x31 Casorati
-    matrices), PGURE lambda search, ARPS on — generic shared-memory SVD + unfused evaluation kernels."""
+    matrices), PGURE lambda search, ARPS on.  rank_cache 0: warp-per-matrix register SVD + truncated factor cache
+    (compact.cuh); 1: the same with a single cached triplet, so that probes overflow into the exact chunked fallback;
+    -1: full factor cache + unfused evaluation kernels."""
     X, _ = synthetic_sequence(32, 33, seed=5)
     args = dict(trajectory_length=31, patch_size=8, optimize_pgure=True, lambda1=-1.0, noise_alpha=0.1, noise_mu=0.05,
                 noise_sigma=0.05, random_seed=1)  # interior optimum (lambda ~ 36.9) rather than the upper bound
     t = 16
-    h = bridge.Handle(X, frame_begin=t, frame_end=t + 1, **args)
+    h = bridge.Handle(X, frame_begin=t, frame_end=t + 1, rank_cache=rank_cache, **args)
     h.process()
     Yh, eh = h.download()
+    st = h.stats()
     h.close()
     ref, est = orc.pguresvt(X, frame_begin=t, frame_end=t + 1, **args)
     assert abs(eh[t, 0] - est[t, 0]) / abs(est[t, 0]) < LAM_TOL
     assert np.abs(Yh[:, :, t] - ref[:, :, t]).max() / np.abs(ref[:, :, t]).max() < 1e-4
+    if rank_cache == 1:
+        assert st["overflow_patches"] > 0 and st["rank_cache"] == 1
+    if rank_cache == -1:
+        assert st["rank_cache"] == 0
+
+
+@pytest.mark.parametrize("svd_kernel", [0, 1])
+@pytest.mark.parametrize("obj", [0, 2, 3])
+def test_config5_shape_singular_values_vs_lapack(svd_kernel, obj):
+    """64x31 Casorati matrices: warp-per-matrix register Jacobi (svd_kernel 0) and shared-memory Jacobi (1), both with the
+    compact epilogue, against LAPACK on the same (perturbed) window."""
+    X, _ = synthetic_sequence(32, 33, seed=5)
+    t, fw = 16, 15
+    h = bridge.Handle(X, trajectory_length=31, patch_size=8, optimize_pgure=True, noise_alpha=0.1, noise_mu=0.05,
+                      noise_sigma=0.05, random_seed=1, svd_kernel=svd_kernel, motion_estimation=False)
+    S = h.probe_singular_values(t, obj)
+    h.close()
+    u = X[:, :, t - fw:t + fw + 1].astype(np.float64)
+    u /= u.max()
+    if obj:
+        _, d2 = orc.perturbations(1, u.size)
+        d2 = d2.reshape(u.shape, order="F")
+        u = u + (d2 * 0.01) if obj == 2 else u - (d2 * 0.01)
+    patches, _, _ = orc.arps(u, 8, t, fw, 7, 33, False)
+    o = orc.SVTObj(patches.astype(np.int64), 32, 31, 8, 1, True)
+    o.decompose(u)
+    So = o.singular_values()
+    assert S.shape == So.shape
+    assert np.abs(S - So).max() / So.max() < 1e-12
+
+
+@pytest.mark.parametrize("svd_kernel,rank_cache", [(0, 0), (0, 2), (1, 0), (1, 1), (0, -1)])
+def test_config5_shape_objective_and_window_vs_oracle(svd_kernel, rank_cache):
+    """PGURE objective (pgure.hpp:120-137) and the reconstructed window (svt.hpp:121-167) of the 64x31 shape at lambdas
+    from 'nothing survives' to 'every triplet survives' — the latter only through the overflow fallback."""
+    X, _ = synthetic_sequence(32, 33, seed=5)
+    t, fw = 16, 15
+    alpha, mu, sigma = 0.1, 0.05, 0.05
+    h = bridge.Handle(X, trajectory_length=31, patch_size=8, optimize_pgure=True, noise_alpha=alpha, noise_mu=mu,
+                      noise_sigma=sigma, random_seed=1, svd_kernel=svd_kernel, rank_cache=rank_cache, motion_estimation=False)
+    lams = np.array([0.0, 0.5, 5.0, 36.9, 99.0])
+    vals, terms = h.probe_pgure(t, alpha, mu, sigma, lams)
+    v = h.probe_reconstruct(t, 36.9)
+    v_all = h.probe_reconstruct(t, 99.0)
+    st = h.stats()
+    h.close()
+    u = X[:, :, t - fw:t + fw + 1].astype(np.float64)
+    u /= u.max()
+    patches, _, _ = orc.arps(u, 8, t, fw, 7, 33, False)
+    Pg = orc.PGUREObj(u, patches.astype(np.int64), alpha, mu, sigma, 8, 1, 1, True, True)  # mu == sigma: the swap of SURVEY Q1 is invisible
+    want = np.array([Pg.calc(l)[0] for l in lams])
+    assert np.abs(vals - want).max() <= 1e-8 * np.abs(want).max(), (vals, want)
+    o = orc.SVTObj(patches.astype(np.int64), 32, 31, 8, 1, True)
+    o.decompose(u)
+    for got, lam in ((v, 36.9), (v_all, 99.0)):
+        vo = o.reconstruct(lam)
+        assert np.abs(got - vo).max() <= 1e-9 * max(1.0, np.abs(vo).max())
+
+
+@pytest.mark.parametrize("rank_cache", [0, 1, 3])
+def test_compact_cache_16x15_matches_golden_objective(golden, rank_cache):
+    """The truncated factor cache on the headline shape (forced through svd_kernel=1): same objective values as the
+    golden vectors, whatever the number of cached triplets."""
+    X = golden["X"]
+    alpha, mu, sigma = golden["pgure_params"]
+    h = bridge.Handle(X, optimize_pgure=True, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1,
+                      svd_kernel=1, rank_cache=rank_cache)
+    vals, terms = h.probe_pgure(8, alpha, mu, sigma, golden["pgure_lambdas"])
+    h.close()
+    assert np.allclose(terms, golden["pgure_terms"], rtol=1e-7, atol=1e-9)
+    assert np.abs(vals - golden["pgure_values"]).max() <= 1e-9 * np.abs(golden["pgure_values"]).max()
 
 
 def test_full_size_properties_1024_pgure():
@@ -531,7 +606,7 @@ def test_full_size_properties_1024_pgure():
     lams = [0.0, 0.05, 0.3, 2.0]
     out = {}
     for k in (0, 1):
-        h = bridge.Handle(X, svd_kernel=k, **kw)
+        h = bridge.Handle(X, svd_kernel=k, rank_cache=-k, **kw)  # k = 1: full factor cache, unfused kernels
         vals, _ = h.probe_pgure(7, 0.05, 0.03, 0.03, lams)
         h.process()
         Y, e = h.download()
