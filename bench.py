@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(float(os.environ.get("PGS_BENCH_SAMPLER_PERIOD", "0.2")))
 
     def summary(self):
         s = sorted(self.samples)
@@ -266,6 +266,10 @@ def main():
     frames = fps_step * world * args.steps
     value = frames / dt
     e2e = frames / dt_e2e
+    if os.environ.get("PGS_BENCH_DEBUG"):
+        print(f"[rank {rank}] ms_per_step {dt / args.steps * 1e3:.1f} stages " +
+              json.dumps({k: round(v / max(nst['n'], 1), 1) for k, v in acc.items() if k.startswith('ms_') or k == 'evals'}),
+              file=sys.stderr)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -1399,22 +1399,46 @@ extern "C" int pguresvt_get_stats(const pguresvt_handle *h, double *stats)
 // ------------------------------------------------------------------------------------------------------
 // one-shot entry points
 // ------------------------------------------------------------------------------------------------------
+// One-shot entry: the whole sequence through one handle when its frames, medians and outputs fit comfortably in HBM,
+// otherwise streamed in contiguous blocks of frames (each with its fw halo frames, exactly like one slice of
+// pguresvt::parallel, utils.hpp:150-166) so that very long / very large sequences never have to be resident at once
+// (the reference keeps the whole sequence and its output in host RAM, pguresvt.hpp:44-67).
+// PGURESVT_BLOCK_FRAMES forces a block length (tests).
 static int run_any(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, const pguresvt_params *p,
                    double *Y, double *estimates)
 {
     if (!X || !Y || !estimates || !p)
         return fail(PGS_ERR_ARG, "null argument");
-    pguresvt_handle *h = pguresvt_create(dtype, n_rows, n_cols, n_frames, p, 0, n_frames);
-    if (!h)
-        return g_err.find("CUDA") != std::string::npos ? PGS_ERR_CUDA : PGS_ERR_ARG;
-    int rc = pguresvt_upload(h, X);
-    if (!rc)
-        rc = pguresvt_process(h);
-    if (!rc)
-        rc = pguresvt_download(h, Y, estimates);
-    const std::string keep = g_err;
-    pguresvt_destroy(h);
-    g_err = keep;
+    uint32_t block = n_frames;
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && p->device >= 0 && p->device < ndev && cudaSetDevice(p->device) == cudaSuccess)
+        {
+            size_t freeb = 0, totb = 0;
+            const size_t per_frame = (size_t)n_rows * n_cols * (dtype_size(dtype) + sizeof(uint16_t) + sizeof(double));
+            if (cudaMemGetInfo(&freeb, &totb) == cudaSuccess && per_frame > 0 && (size_t)n_frames * per_frame > freeb / 4)
+                block = (uint32_t)std::max<size_t>(1, (freeb / 4) / per_frame);
+        }
+        if (const char *e = getenv("PGURESVT_BLOCK_FRAMES"))
+            if (atoi(e) > 0)
+                block = (uint32_t)atoi(e);
+    }
+    int rc = PGS_OK;
+    for (uint32_t fb = 0; (fb < n_frames || fb == 0) && !rc; fb += block)
+    { // (an empty sequence still goes through pguresvt_create once for its error message)
+        const uint32_t fe = (uint32_t)std::min<uint64_t>((uint64_t)fb + block, n_frames);
+        pguresvt_handle *h = pguresvt_create(dtype, n_rows, n_cols, n_frames, p, fb, fe);
+        if (!h)
+            return g_err.find("CUDA") != std::string::npos ? PGS_ERR_CUDA : PGS_ERR_ARG;
+        rc = pguresvt_upload(h, X);
+        if (!rc)
+            rc = pguresvt_process(h);
+        if (!rc)
+            rc = pguresvt_download(h, Y, estimates);
+        const std::string keep = g_err;
+        pguresvt_destroy(h);
+        g_err = keep;
+    }
     return rc;
 }
 extern "C" int pguresvt_run_u8(const uint8_t *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y, double *e)

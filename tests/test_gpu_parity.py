@@ -285,6 +285,18 @@ def test_frame_block_equals_full_run():
         h.close()
 
 
+def test_one_shot_entry_streams_blocks(monkeypatch):
+    """The one-shot C entry streams a long sequence in blocks of frames: forcing 5-frame blocks must
+    give the result of the single-handle run (each block carries its halo frames and applies the global edge rules)."""
+    X, _ = synthetic_sequence(32, 23, seed=9)
+    kw = dict(optimize_pgure=True, lambda1=-1.0, noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03, random_seed=1)
+    Y0, e0, _ = bridge.pguresvt_u16(X, **kw)
+    monkeypatch.setenv("PGURESVT_BLOCK_FRAMES", "5")
+    Y1, e1, _ = bridge.pguresvt_u16(X, **kw)
+    assert np.abs(e1 - e0).max() <= 1e-9 * np.abs(e0).max()
+    assert np.abs(Y1 - Y0).max() <= 1e-9 * np.abs(Y0).max()
+
+
 def test_idempotent_and_deterministic_fixed_lambda():
     X, _ = synthetic_sequence(32, 16, seed=17)
     a = SVT(optimize_pgure=False, lambda1=0.15).denoise(X).Y_
