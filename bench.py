@@ -132,6 +132,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # libraries (NCCL prints its version banner on stdout) must not pollute the ONE JSON line: everything written to fd 1
+    # goes to stderr from here on, the result line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -164,7 +174,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "impl": "reference", "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -340,7 +350,7 @@ def main():
             line["cpu_baseline"], _ = cpu_reference(args, size, dict(kw))
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
