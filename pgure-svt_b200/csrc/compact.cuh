@@ -19,8 +19,8 @@
 // rotation (round E pairs slots (2p, 2p+1), round O pairs (2p+1, 2p+2); the rotated columns are written back exchanged),
 // so every pair of columns meets exactly once in 32 rounds and the schedule needs NO register moves and only two round
 // bodies — the loop stays inside the instruction cache.  Per round: 16 partial inner products per lane, one transposing
-// butterfly (16 double shuffles) that leaves pair p's sum on lanes 2p, 2p+1, one rotation per lane from TRACKED squared
-// norms (jacobi_cs_track, refreshed once per sweep), (c, s) of the 16 pairs broadcast through shared memory.
+// butterfly (16 double shuffles) that leaves pair p's sum on lanes 2p, 2p+1, one fast (scaled) rotation per lane from TRACKED
+// squared norms (jacobi_fast_givens, norms refreshed once per sweep), its two coefficients broadcast through shared memory.
 // V is not accumulated: V = A0^T U / sigma is rebuilt from the re-gathered matrix at the end (as in k_svd16_l4), fused
 // with the q-forms.  Replaces arma::svd_econ (svt.hpp:111) for bs = 8 (64 x 15 ... 64 x 31).
 #pragma once
@@ -94,17 +94,20 @@ struct SvdOut
     double *fac;
     size_t rec;
     int ldv;
-    double *S;        // 32 doubles per patch, descending (svt.hpp:111 order), zero padded
-    double *Q;        // 32 doubles per patch: q_k in the same order
+    double *S[3];     // per object: 32 doubles per patch, descending (svt.hpp:111 order), zero padded
+    double *Q[3];     // per object: 32 doubles per patch: q_k in the same order
     double *lead;     // R x (m + 32) doubles per patch: u_k (m) | v_k (32, zero padded)
     int R;
     const double *c4; // delta2 / weights per voxel (k_c4)
 };
 
-// one round of the odd-even ordering; ODD = 0: slot pairs (2p, 2p+1), p = 0..15; ODD = 1: (2p+1, 2p+2), p = 0..14
+// one round of the odd-even ordering; ODD = 0: slot pairs (2p, 2p+1), p = 0..15; ODD = 1: (2p+1, 2p+2), p = 0..14.
+// Lane l holds the state of the column in slot l: its tracked TRUE squared norm and — fast (scaled) rotations as in
+// k_svd16_l4 — the scale of the stored column and its reciprocal (true column = sc * stored column), so that a rotation
+// costs two FMAs per element pair:  x' = x - alpha y,  y' = y + beta x  (jacobi_fast_givens).
 template <int RPL, int ODD>
-__device__ __forceinline__ void svdw_round(double (&a)[RPL][32], double &nrm, double2 *csb, int lane, double tol2, double big2,
-                                           bool &big)
+__device__ __forceinline__ void svdw_round(double (&a)[RPL][32], double &nrm, double &sc, double &isc, double2 *csb, int lane,
+                                           double tol2, double big2, bool &big)
 {
     double pg[16];
 #pragma unroll
@@ -122,42 +125,56 @@ __device__ __forceinline__ void svdw_round(double (&a)[RPL][32], double &nrm, do
     double G = trw_16(pg, lane); // pair p on lanes 2p, 2p+1
     if (ODD)
         G = __shfl_up_sync(0xffffffffu, G, 1); // pair p on lanes 2p+1 (its low slot) and 2p+2 (its high slot)
-    // lane l holds the tracked squared norm of the column in slot l
     const bool is_lo = ((lane & 1) == ODD);
     const bool active = ODD ? (lane >= 1 && lane <= 30) : true;
-    const double other = __shfl_sync(0xffffffffu, nrm, (is_lo ? lane + 1 : lane - 1) & 31);
-    double A = is_lo ? nrm : other, B = is_lo ? other : nrm;
+    const int partner = (is_lo ? lane + 1 : lane - 1) & 31;
+    const double o_nrm = __shfl_sync(0xffffffffu, nrm, partner);
+    const double o_sc = __shfl_sync(0xffffffffu, sc, partner);
+    const double o_isc = __shfl_sync(0xffffffffu, isc, partner);
+    double A = is_lo ? nrm : o_nrm, B = is_lo ? o_nrm : nrm;
+    double sx = is_lo ? sc : o_sc, sy = is_lo ? o_sc : sc;
+    double isx = is_lo ? isc : o_isc, isy = is_lo ? o_isc : isc;
     if (!active)
     {
         G = 0.0;
-        A = B = 1.0;
+        A = B = sx = sy = isx = isy = 1.0;
     }
-    double c, s;
+    double alpha, beta;
     bool bg = false;
-    jacobi_cs_track(A, B, G, tol2, big2, c, s, bg); // both lanes of a pair derive the identical rotation
+    jacobi_fast_givens(A, B, sx, sy, isx, isy, G, tol2, big2, alpha, beta, bg); // both lanes of a pair derive the identical rotation
     big = big || bg;
-    // the rotated columns are written back exchanged: the low slot receives y' (norm B), the high slot x' (norm A)
+    // the rotated columns are written back exchanged: the low slot receives y' (norm B, scale sy), the high slot x'
     if (active)
+    {
         nrm = is_lo ? B : A;
+        sc = is_lo ? sy : sx;
+        isc = is_lo ? isy : isx;
+    }
     if (is_lo && active)
-        csb[(lane - ODD) >> 1] = make_double2(c, s);
+        csb[(lane - ODD) >> 1] = make_double2(alpha, beta);
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < 16 - ODD; p++)
     {
-        const double2 cs = csb[p];
+        const double2 ab = csb[p];
 #pragma unroll
         for (int r = 0; r < RPL; r++)
         {
             const double x = a[r][2 * p + ODD], y = a[r][2 * p + ODD + 1];
-            a[r][2 * p + ODD] = fma(cs.y, x, cs.x * y);      // y' = s x + c y
-            a[r][2 * p + ODD + 1] = fma(cs.x, x, -cs.y * y); // x' = c x - s y
+            a[r][2 * p + ODD] = fma(ab.y, x, y);      // y' = y + beta x
+            a[r][2 * p + ODD + 1] = fma(-ab.x, y, x); // x' = x - alpha y
         }
     }
 }
 
-#define SVDW_WARP_DOUBLES(RPL) (32 * (RPL)*32 + 64) /* W staging (m x 32) | two (c, s) buffers of 16 double2 */
+#define SVDW_WARP_DOUBLES(RPL) (32 * (RPL)*32 + 32 * 32 + 64) /* W staging (m x 32) | V of object U (32 x 32) | two coefficient buffers of 16 double2 */
 
+// MODE 0: one SVT object (pt.mode), full records.  MODE 1: one object, compact cache (o.S[0], o.Q[0], o.lead).
+// MODE 2: the three PGURE objects U, U + eps2*delta2, U - eps2*delta2 of a patch back to back by the same warp
+// (o.S[i], o.Q[i]; pt.eps = eps2): the perturbed matrices are WARM-STARTED — multiplied by the V of object U, which
+// never leaves shared memory — so their Jacobi iteration starts from nearly orthogonal columns (the same idea as
+// k_svd16_l4<WARM>, without the round trip of V through HBM and without the perturbed-window copies).  A rank-deficient
+// object U (a zero patch, say) has no orthogonal V to offer: its perturbed objects start cold.
 template <int RPL, int MODE>
 __global__ void __launch_bounds__(128, 2)
     k_svd_warp(const double *__restrict__ u, Perturb pt, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
@@ -170,7 +187,8 @@ __global__ void __launch_bounds__(128, 2)
     if (pidx >= P) // warp-uniform; the kernel has no CTA-wide barrier
         return;
     double *Ws = smw + (size_t)wib * SVDW_WARP_DOUBLES(RPL);
-    double2 *csb = reinterpret_cast<double2 *>(Ws + M * 32);
+    double *V0s = Ws + M * 32; // V of object U: V0s[s * 32 + k] = V(k, slot s)
+    double2 *csb = reinterpret_cast<double2 *>(V0s + 32 * 32);
     const int id = ids[pidx];
     const size_t fsz = (size_t)N * N;
     int myoff = 0; // offset of slice `lane`'s block origin within its slice (svt.hpp:99-109)
@@ -186,22 +204,92 @@ __global__ void __launch_bounds__(128, 2)
         const int e = lane + 32 * r;
         eoff[r] = (e % bs) + N * (e / bs);
     }
-    double a[RPL][32];
-#pragma unroll
-    for (int k = 0; k < 32; k++)
-    {
-        const int offk = __shfl_sync(0xffffffffu, myoff, k);
-#pragma unroll
-        for (int r = 0; r < RPL; r++)
-            a[r][k] = (k < n) ? load_perturbed(u, (size_t)offk + eoff[r] + fsz * k, pt) : 0.0;
-    }
-
-    int sweep = 0, quiet = 0;
-    double nrm = 0.0;
+    bool warm_ok = false;
 #pragma unroll 1
-    for (; sweep < max_sweeps;)
+    for (int oi = 0; oi < (MODE == 2 ? 3 : 1); oi++)
     {
-        { // fresh squared norms at the start of every sweep (the tracked updates drift by rounding only)
+        if (MODE == 2)
+            pt.mode = (oi == 0) ? 0 : oi + 1;
+        double a[RPL][32];
+#pragma unroll
+        for (int k = 0; k < 32; k++)
+        {
+            const int offk = __shfl_sync(0xffffffffu, myoff, k);
+#pragma unroll
+            for (int r = 0; r < RPL; r++)
+                a[r][k] = (k < n) ? load_perturbed(u, (size_t)offk + eoff[r] + fsz * k, pt) : 0.0;
+        }
+        if (MODE == 2 && oi > 0 && warm_ok)
+        { // rows of A times V0: the register file never holds more than one row twice
+#pragma unroll
+            for (int r = 0; r < RPL; r++)
+            {
+                double t[32];
+#pragma unroll
+                for (int s = 0; s < 32; s++)
+                {
+                    const double2 *vs = reinterpret_cast<const double2 *>(V0s + s * 32);
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; k2++)
+                    {
+                        const double2 v = vs[k2];
+                        acc = fma(a[r][2 * k2], v.x, acc);
+                        acc = fma(a[r][2 * k2 + 1], v.y, acc);
+                    }
+                    t[s] = acc;
+                }
+#pragma unroll
+                for (int s = 0; s < 32; s++)
+                    a[r][s] = t[s];
+            }
+        }
+
+        int sweep = 0, quiet = 0;
+        double nrm = 0.0, sc = 1.0, isc = 1.0;
+#pragma unroll 1
+        for (; sweep < max_sweeps;)
+        {
+            { // fresh squared norms at the start of every sweep (the tracked updates drift by rounding only)
+                double n2[32];
+#pragma unroll
+                for (int s = 0; s < 32; s++)
+                {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int r = 0; r < RPL; r++)
+                        sacc = fma(a[r][s], a[r][s], sacc);
+                    n2[s] = sacc;
+                }
+                nrm = trw_32(n2, lane) * (sc * sc);
+            }
+#pragma unroll 1
+            for (int rp = 0; rp < 16 && quiet < 32; rp++)
+            {
+                bool big = false;
+                svdw_round<RPL, 0>(a, nrm, sc, isc, csb, lane, tol2, big2, big);
+                quiet = __any_sync(0xffffffffu, big) ? 0 : quiet + 1;
+                big = false;
+                svdw_round<RPL, 1>(a, nrm, sc, isc, csb + 16, lane, tol2, big2, big);
+                quiet = __any_sync(0xffffffffu, big) ? 0 : quiet + 1;
+            }
+            sweep++;
+            if (quiet >= 32) // every pair met once in the last 32 rounds and none needed a rotation above `big`
+                break;
+        }
+
+        // true columns = scale * stored columns; the scale of slot s sits in lane s
+#pragma unroll
+        for (int s = 0; s < 32; s++)
+        {
+            const double ss = __shfl_sync(0xffffffffu, sc, s);
+#pragma unroll
+            for (int r = 0; r < RPL; r++)
+                a[r][s] *= ss;
+        }
+        // singular values: lane s owns slot s
+        double my2;
+        {
             double n2[32];
 #pragma unroll
             for (int s = 0; s < 32; s++)
@@ -212,145 +300,128 @@ __global__ void __launch_bounds__(128, 2)
                     sacc = fma(a[r][s], a[r][s], sacc);
                 n2[s] = sacc;
             }
-            nrm = trw_32(n2, lane);
+            my2 = trw_32(n2, lane);
         }
-#pragma unroll 1
-        for (int rp = 0; rp < 16 && quiet < 32; rp++)
+        const double sig = sqrt(my2);
+        int rk = 0; // descending order like LAPACK (svt.hpp:111); ties by slot
+#pragma unroll
+        for (int t = 0; t < 32; t++)
         {
-            bool big = false;
-            svdw_round<RPL, 0>(a, nrm, csb, lane, tol2, big2, big);
-            quiet = __any_sync(0xffffffffu, big) ? 0 : quiet + 1;
-            big = false;
-            svdw_round<RPL, 1>(a, nrm, csb + 16, lane, tol2, big2, big);
-            quiet = __any_sync(0xffffffffu, big) ? 0 : quiet + 1;
+            const double st = __shfl_sync(0xffffffffu, sig, t);
+            rk += (st > sig || (st == sig && t < lane)) ? 1 : 0;
         }
-        sweep++;
-        if (quiet >= 32) // every pair met once in the last 32 rounds and none needed a rotation above `big`
-            break;
-    }
-
-    // singular values: lane s owns slot s
-    double my2;
-    {
-        double n2[32];
+        const double inv = (sig > 0.0) ? 1.0 / sig : 0.0;
+        // W = U diag(sigma) staged in shared memory (column s at Ws + s*M); the registers of `a` are dead from here on
+        __syncwarp();
 #pragma unroll
         for (int s = 0; s < 32; s++)
-        {
-            double sacc = 0.0;
 #pragma unroll
             for (int r = 0; r < RPL; r++)
-                sacc = fma(a[r][s], a[r][s], sacc);
-            n2[s] = sacc;
-        }
-        my2 = trw_32(n2, lane);
-    }
-    const double sig = sqrt(my2);
-    int rk = 0; // descending order like LAPACK (svt.hpp:111); ties by slot
-#pragma unroll
-    for (int t = 0; t < 32; t++)
-    {
-        const double st = __shfl_sync(0xffffffffu, sig, t);
-        rk += (st > sig || (st == sig && t < lane)) ? 1 : 0;
-    }
-    const double inv = (sig > 0.0) ? 1.0 / sig : 0.0;
-    // W = U diag(sigma) staged in shared memory (column s at Ws + s*M); the registers of `a` are dead from here on
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 32; s++)
-#pragma unroll
-        for (int r = 0; r < RPL; r++)
-            Ws[s * M + lane + 32 * r] = a[r][s];
-    __syncwarp();
-    // lane k re-gathers column k of the decomposed matrix A0 (and of C4) and contracts it with every W column:
-    //   vw[s] = A0(:,k) . w_s = sigma_s^2 v_s[k],   cw[s] = C4(:,k) . w_s   (q_s = sum_k vw[s] cw[s] / sigma_s^3)
-    double vw[32], cw[32];
-#pragma unroll
-    for (int s = 0; s < 32; s++)
-        vw[s] = cw[s] = 0.0;
-    const bool realcol = lane < n;
-    const size_t colbase = (size_t)myoff + fsz * lane;
-#pragma unroll 1
-    for (int e0 = 0; e0 < M; e0 += 8)
-    {
-        double a0[8], c0[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-        {
-            const int e = e0 + i;
-            const size_t vox = colbase + (e % bs) + (size_t)N * (e / bs);
-            a0[i] = realcol ? load_perturbed(u, vox, pt) : 0.0;
-            c0[i] = (MODE == 1 && realcol) ? o.c4[vox] : 0.0;
-        }
+                Ws[s * M + lane + 32 * r] = a[r][s];
+        __syncwarp();
+        // lane k re-gathers column k of the decomposed matrix A0 (and of C4) and contracts it with every W column:
+        //   vw[s] = A0(:,k) . w_s = sigma_s^2 v_s[k],   cw[s] = C4(:,k) . w_s   (q_s = sum_k vw[s] cw[s] / sigma_s^3)
+        double vw[32], cw[32];
 #pragma unroll
         for (int s = 0; s < 32; s++)
+            vw[s] = cw[s] = 0.0;
+        const bool realcol = lane < n;
+        const size_t colbase = (size_t)myoff + fsz * lane;
+#pragma unroll 1
+        for (int e0 = 0; e0 < M; e0 += 8)
         {
-            const double2 *wp = reinterpret_cast<const double2 *>(Ws + s * M + e0);
+            double a0[8], c0[8];
 #pragma unroll
-            for (int i2 = 0; i2 < 4; i2++)
+            for (int i = 0; i < 8; i++)
             {
-                const double2 w = wp[i2];
-                vw[s] = fma(a0[2 * i2], w.x, vw[s]);
-                vw[s] = fma(a0[2 * i2 + 1], w.y, vw[s]);
-                if (MODE == 1)
+                const int e = e0 + i;
+                const size_t vox = colbase + (e % bs) + (size_t)N * (e / bs);
+                a0[i] = realcol ? load_perturbed(u, vox, pt) : 0.0;
+                c0[i] = (MODE != 0 && realcol) ? o.c4[vox] : 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < 32; s++)
+            {
+                const double2 *wp = reinterpret_cast<const double2 *>(Ws + s * M + e0);
+#pragma unroll
+                for (int i2 = 0; i2 < 4; i2++)
                 {
-                    cw[s] = fma(c0[2 * i2], w.x, cw[s]);
-                    cw[s] = fma(c0[2 * i2 + 1], w.y, cw[s]);
+                    const double2 w = wp[i2];
+                    vw[s] = fma(a0[2 * i2], w.x, vw[s]);
+                    vw[s] = fma(a0[2 * i2 + 1], w.y, vw[s]);
+                    if (MODE != 0)
+                    {
+                        cw[s] = fma(c0[2 * i2], w.x, cw[s]);
+                        cw[s] = fma(c0[2 * i2 + 1], w.y, cw[s]);
+                    }
                 }
             }
         }
-    }
-    if (MODE == 1)
-    {
-        double pr[32];
-#pragma unroll
-        for (int s = 0; s < 32; s++)
-            pr[s] = vw[s] * cw[s];
-        const double qs = trw_32(pr, lane) * (inv * inv * inv);
-        o.S[(size_t)pidx * 32 + rk] = sig;
-        o.Q[(size_t)pidx * 32 + rk] = qs;
-        if (o.lead && o.R > 0)
+        if (MODE != 0)
         {
-            double *L = o.lead + (size_t)pidx * o.R * (M + 32);
+            double pr[32];
+#pragma unroll
+            for (int s = 0; s < 32; s++)
+                pr[s] = vw[s] * cw[s];
+            const double qs = trw_32(pr, lane) * (inv * inv * inv);
+            double *So = (oi == 0) ? o.S[0] : (oi == 1) ? o.S[1] : o.S[2];
+            double *Qo = (oi == 0) ? o.Q[0] : (oi == 1) ? o.Q[1] : o.Q[2];
+            So[(size_t)pidx * 32 + rk] = sig;
+            Qo[(size_t)pidx * 32 + rk] = qs;
+            const bool want_lead = oi == 0 && o.lead && o.R > 0;
+            if (want_lead || (MODE == 2 && oi == 0))
+            {
+                double *L = want_lead ? o.lead + (size_t)pidx * o.R * (M + 32) : nullptr;
+#pragma unroll
+                for (int s = 0; s < 32; s++)
+                {
+                    const int rks = __shfl_sync(0xffffffffu, rk, s);
+                    const double invs = __shfl_sync(0xffffffffu, inv, s);
+                    const double vks = vw[s] * (invs * invs); // V(lane, slot s)
+                    if (want_lead && rks < o.R)
+                    {
+                        double *Lk = L + (size_t)rks * (M + 32);
+#pragma unroll
+                        for (int r = 0; r < RPL; r++)
+                            Lk[lane + 32 * r] = Ws[s * M + lane + 32 * r] * invs;
+                        Lk[M + lane] = vks;
+                    }
+                    if (MODE == 2)
+                        V0s[s * 32 + lane] = vks;
+                }
+                if (MODE == 2)
+                { // V0 is orthogonal on the n real columns only if object U has full column rank
+                    const double smax = warp_max(sig);
+                    warm_ok = __popc(__ballot_sync(0xffffffffu, sig > smax * 1e-8)) >= n;
+                    __syncwarp();
+                }
+            }
+        }
+        else
+        {
+            double *R = o.fac + o.rec * (size_t)pidx;
 #pragma unroll
             for (int s = 0; s < 32; s++)
             {
                 const int rks = __shfl_sync(0xffffffffu, rk, s);
                 const double invs = __shfl_sync(0xffffffffu, inv, s);
-                if (rks < o.R)
+                if (rks < n)
                 {
-                    double *Lk = L + (size_t)rks * (M + 32);
 #pragma unroll
                     for (int r = 0; r < RPL; r++)
-                        Lk[lane + 32 * r] = Ws[s * M + lane + 32 * r] * invs;
-                    Lk[M + lane] = vw[s] * (invs * invs);
+                        R[(size_t)M * rks + lane + 32 * r] = Ws[s * M + lane + 32 * r] * invs;
+                    if (lane < o.ldv)
+                        R[(size_t)M * n + (size_t)o.ldv * rks + lane] = vw[s] * (invs * invs);
                 }
             }
+            if (rk < n)
+                R[(size_t)M * n + (size_t)o.ldv * n + rk] = sig;
         }
-    }
-    else
-    {
-        double *R = o.fac + o.rec * (size_t)pidx;
-#pragma unroll
-        for (int s = 0; s < 32; s++)
+        if (sweeps_out && lane == 0)
         {
-            const int rks = __shfl_sync(0xffffffffu, rk, s);
-            const double invs = __shfl_sync(0xffffffffu, inv, s);
-            if (rks < n)
-            {
-#pragma unroll
-                for (int r = 0; r < RPL; r++)
-                    R[(size_t)M * rks + lane + 32 * r] = Ws[s * M + lane + 32 * r] * invs;
-                if (lane < o.ldv)
-                    R[(size_t)M * n + (size_t)o.ldv * rks + lane] = vw[s] * (invs * invs);
-            }
+            atomicMax(sweeps_out, sweep);
+            atomicAdd(sweeps_out + 1 + (oi > 0 ? 1 : 0), sweep);
         }
-        if (rk < n)
-            R[(size_t)M * n + (size_t)o.ldv * n + rk] = sig;
-    }
-    if (sweeps_out && lane == 0)
-    {
-        atomicMax(sweeps_out, sweep);
-        atomicAdd(sweeps_out + 1, sweep);
     }
 }
 
@@ -475,8 +546,8 @@ __global__ void k_svd_smem_c(const double *__restrict__ u, Perturb pt, const sho
     }
     if (lane < n)
     {
-        o.S[(size_t)pidx * 32 + rk] = sj;
-        o.Q[(size_t)pidx * 32 + rk] = qmine * inv;
+        o.S[0][(size_t)pidx * 32 + rk] = sj;
+        o.Q[0][(size_t)pidx * 32 + rk] = qmine * inv;
     }
     if (o.lead && o.R > 0)
     {
