@@ -210,39 +210,55 @@ __global__ void __launch_bounds__(128, 2)
     {
         if (MODE == 2)
             pt.mode = (oi == 0) ? 0 : oi + 1;
+        // Casorati gather (svt.hpp:99-109) through shared memory in a ROLLED loop: the perturbation code exists once instead
+        // of 64 times (the straight-line version was 110 KB of instructions, fetched once per matrix and never reused —
+        // ncu: 29 % of the stalls were "no instruction")
         double a[RPL][32];
-#pragma unroll
-        for (int k = 0; k < 32; k++)
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < n; k++)
         {
             const int offk = __shfl_sync(0xffffffffu, myoff, k);
 #pragma unroll
             for (int r = 0; r < RPL; r++)
-                a[r][k] = (k < n) ? load_perturbed(u, (size_t)offk + eoff[r] + fsz * k, pt) : 0.0;
+                Ws[k * M + lane + 32 * r] = load_perturbed(u, (size_t)offk + eoff[r] + fsz * k, pt);
         }
-        if (MODE == 2 && oi > 0 && warm_ok)
-        { // rows of A times V0: the register file never holds more than one row twice
+#pragma unroll
+        for (int k = 0; k < 32; k++)
 #pragma unroll
             for (int r = 0; r < RPL; r++)
+                a[r][k] = (k < n) ? Ws[k * M + lane + 32 * r] : 0.0; // own writes only: no barrier needed
+        if (MODE == 2 && oi > 0 && warm_ok)
+        { // rows of A times V0, one slot per iteration of a rolled loop, results parked in the (free) W buffer
+            __syncwarp();
+#pragma unroll 1
+            for (int s = 0; s < 32; s++)
             {
-                double t[32];
+                const double2 *vs = reinterpret_cast<const double2 *>(V0s + s * 32);
+                double acc[RPL];
 #pragma unroll
-                for (int s = 0; s < 32; s++)
+                for (int r = 0; r < RPL; r++)
+                    acc[r] = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++)
                 {
-                    const double2 *vs = reinterpret_cast<const double2 *>(V0s + s * 32);
-                    double acc = 0.0;
+                    const double2 v = vs[k2];
 #pragma unroll
-                    for (int k2 = 0; k2 < 16; k2++)
+                    for (int r = 0; r < RPL; r++)
                     {
-                        const double2 v = vs[k2];
-                        acc = fma(a[r][2 * k2], v.x, acc);
-                        acc = fma(a[r][2 * k2 + 1], v.y, acc);
+                        acc[r] = fma(a[r][2 * k2], v.x, acc[r]);
+                        acc[r] = fma(a[r][2 * k2 + 1], v.y, acc[r]);
                     }
-                    t[s] = acc;
                 }
 #pragma unroll
-                for (int s = 0; s < 32; s++)
-                    a[r][s] = t[s];
+                for (int r = 0; r < RPL; r++)
+                    Ws[s * M + lane + 32 * r] = acc[r];
             }
+#pragma unroll
+            for (int s = 0; s < 32; s++)
+#pragma unroll
+                for (int r = 0; r < RPL; r++)
+                    a[r][s] = Ws[s * M + lane + 32 * r];
         }
 
         int sweep = 0, quiet = 0;
@@ -328,11 +344,11 @@ __global__ void __launch_bounds__(128, 2)
         const bool realcol = lane < n;
         const size_t colbase = (size_t)myoff + fsz * lane;
 #pragma unroll 1
-        for (int e0 = 0; e0 < M; e0 += 8)
-        {
-            double a0[8], c0[8];
+        for (int e0 = 0; e0 < M; e0 += 2)
+        { // two rows per iteration (one 16-byte broadcast read per W column); kept rolled for the instruction cache
+            double a0[2], c0[2];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 2; i++)
             {
                 const int e = e0 + i;
                 const size_t vox = colbase + (e % bs) + (size_t)N * (e / bs);
@@ -342,18 +358,13 @@ __global__ void __launch_bounds__(128, 2)
 #pragma unroll
             for (int s = 0; s < 32; s++)
             {
-                const double2 *wp = reinterpret_cast<const double2 *>(Ws + s * M + e0);
-#pragma unroll
-                for (int i2 = 0; i2 < 4; i2++)
+                const double2 w = *reinterpret_cast<const double2 *>(Ws + s * M + e0);
+                vw[s] = fma(a0[0], w.x, vw[s]);
+                vw[s] = fma(a0[1], w.y, vw[s]);
+                if (MODE != 0)
                 {
-                    const double2 w = wp[i2];
-                    vw[s] = fma(a0[2 * i2], w.x, vw[s]);
-                    vw[s] = fma(a0[2 * i2 + 1], w.y, vw[s]);
-                    if (MODE != 0)
-                    {
-                        cw[s] = fma(c0[2 * i2], w.x, cw[s]);
-                        cw[s] = fma(c0[2 * i2 + 1], w.y, cw[s]);
-                    }
+                    cw[s] = fma(c0[0], w.x, cw[s]);
+                    cw[s] = fma(c0[1], w.y, cw[s]);
                 }
             }
         }

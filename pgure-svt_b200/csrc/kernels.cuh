@@ -1191,9 +1191,21 @@ __global__ void __launch_bounds__(128, 2)
         cp_async_wait<0>();
         __syncwarp();
         const double *V0 = sv0 + (size_t)(threadIdx.x >> 2) * SVD16_V0_STRIDE;
+        // V0 is orthogonal only if object 0 has full column rank (its V is rebuilt as A^T U / sigma, so a vanishing sigma
+        // leaves a zero column — a zero patch, say): such a matrix starts cold instead
+        bool v0_ok;
+        {
+            const double *S0 = fac0 + (size_t)SVD16_REC * pidx + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+            double lo = fmin(fmin(S0[4 * sub], S0[4 * sub + 1]), fmin(S0[4 * sub + 2], (sub == 3) ? S0[4 * sub + 2] : S0[4 * sub + 3]));
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, 1));
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, 2));
+            v0_ok = lo > S0[15] * 1e-8;
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
+            if (!v0_ok)
+                break;
 #pragma unroll 1
             for (int j = 0; j < SVD16_N; j++)
             {

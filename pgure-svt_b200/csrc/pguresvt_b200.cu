@@ -71,6 +71,7 @@ struct pguresvt_handle
     bool use_l4 = false;      // 4-lanes-per-matrix kernel (S in slot order, S[15] = sigma_max)
     bool use_fused_eval = false;
     bool use_warp_svd = false; // 64 x n Casorati matrices: warp-per-matrix register Jacobi (compact.cuh)
+    bool use_warp3 = false;    // compact cache + warp kernel: the three PGURE objects of a patch in one launch, warm-started
     bool use_compact = false;  // truncated factor cache (S, q-forms, leading Rc triplets of object 0), compact.cuh
     int Rc = 0;                // leading singular triplets of object 0 kept per patch
     int evc_warps = 0;         // warps of the k_eval_c grid (one s4 partial each)
@@ -272,6 +273,7 @@ static int create_impl(pguresvt_handle *h)
     h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
     // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
     h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
+    h->use_warp3 = h->use_compact && h->use_warp_svd && !getenv("PGURESVT_NO_WARP3");
     {
         const double kappa = 1.;
         h->vP = 0.5 + 0.5 * kappa / std::sqrt(kappa * kappa + 4);
@@ -355,7 +357,7 @@ static int create_impl(pguresvt_handle *h)
     CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
     CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
-    CU(cudaMalloc(&h->dSweeps, 2 * sizeof(int)));
+    CU(cudaMalloc(&h->dSweeps, 4 * sizeof(int)));
     CU(cudaMalloc(&h->dNcost, sizeof(unsigned long long)));
     CU(cudaMallocHost(&h->hOut, 16 * sizeof(double)));
     if (h->use_compact)
@@ -748,9 +750,13 @@ static int launch_svd_generic(pguresvt_handle *h, const Perturb &pt, const int *
         {
             CU(cudaFuncSetAttribute(k_svd_warp<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             CU(cudaFuncSetAttribute(k_svd_warp<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(k_svd_warp<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             h->attr_svdw = true;
         }
-        if (mode == 1)
+        if (mode == 2)
+            k_svd_warp<2, 2><<<cdiv(np, 4), 128, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n, o,
+                                                                 max_sweeps, tol2, big2, h->dSweeps);
+        else if (mode == 1)
             k_svd_warp<2, 1><<<cdiv(np, 4), 128, smem, h->st>>>(h->dU, pt, h->dPos, ids, np, h->vecSize, h->N, h->p.block_size, h->n, o,
                                                                  max_sweeps, tol2, big2, h->dSweeps);
         else
@@ -843,13 +849,23 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         SvdOut o{};
         if (h->use_compact)
         {
-            o.S = h->dSc[obj], o.Q = h->dQc[obj], o.c4 = h->dC4;
+            if (h->use_warp3)
+            { // the three objects of a patch back to back in one launch (perturbed ones warm-started), issued for object 0
+                if (obj != 0)
+                    return fail(PGS_ERR_ARG, "objects 2 and 3 are decomposed together with object 0");
+                o.S[0] = h->dSc[0], o.S[1] = h->dSc[2], o.S[2] = h->dSc[3];
+                o.Q[0] = h->dQc[0], o.Q[1] = h->dQc[2], o.Q[2] = h->dQc[3];
+                pt.eps = 100 * eps1;
+            }
+            else
+                o.S[0] = h->dSc[obj], o.Q[0] = h->dQc[obj];
+            o.c4 = h->dC4;
             o.lead = (obj == 0) ? h->dLead : nullptr;
             o.R = (obj == 0) ? h->Rc : 0;
         }
         else
             o.fac = h->dFac[obj], o.rec = h->rec, o.ldv = h->ldv;
-        int rc = launch_svd_generic(h, pt, h->dIds, h->P, o, h->use_compact ? 1 : 0);
+        int rc = launch_svd_generic(h, pt, h->dIds, h->P, o, h->use_compact ? (h->use_warp3 ? 2 : 1) : 0);
         if (rc)
             return rc;
         h->launches--; // counted once below
@@ -1196,17 +1212,29 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         StageTimer tm(h, 5);
         for (int k = 0; k < h->nobj; k++)
         {
-            CU(cudaMemsetAsync(h->dSweeps, 0, 2 * sizeof(int), h->st));
+            if (h->use_warp3 && h->objs[k] != 0)
+            { // decomposed together with object 0
+                h->stats[1] += h->P;
+                continue;
+            }
+            CU(cudaMemsetAsync(h->dSweeps, 0, 4 * sizeof(int), h->st));
             if ((rc = stage_svd(h, h->objs[k])))
                 return rc;
-            int sw[2] = {0, 0};
-            CU(cudaMemcpyAsync(sw, h->dSweeps, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            int sw[4] = {0, 0, 0, 0};
+            CU(cudaMemcpyAsync(sw, h->dSweeps, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
             CU(cudaStreamSynchronize(h->st));
             h->stats[10] = std::max(h->stats[10], (double)sw[0]);
             // mean sweeps per warp of object 0 ([12]) and of the warm-started objects ([13]) of the last frame
             const double nwarps = std::ceil((double)h->P * (h->use_l4 ? 4 : 8) / 32.0);
             if (h->use_reg_svd && h->use_l4)
                 h->stats[h->objs[k] == 0 ? 12 : 13] = sw[1] / nwarps;
+            if (h->use_warp_svd && h->use_compact)
+            { // one warp per matrix: [1] sums object U (or the only object of the launch), [2] the warm-started ones
+                if (h->use_warp3 || h->objs[k] == 0)
+                    h->stats[12] = sw[1] / (double)h->P;
+                if (h->use_warp3)
+                    h->stats[13] = sw[2] / (2.0 * h->P);
+            }
         }
     }
     if (h->use_fused_eval)

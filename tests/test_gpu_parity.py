@@ -593,6 +593,38 @@ def test_config5_shape_objective_and_window_vs_oracle(svd_kernel, rank_cache):
         assert np.abs(got - vo).max() <= 1e-9 * max(1.0, np.abs(vo).max())
 
 
+@pytest.mark.parametrize("patch,traj,rank_cache", [(4, 15, 0), (8, 31, 0), (8, 31, 2)])
+def test_zero_region_rank_deficient_patches(patch, traj, rank_cache):
+    """A region of exact zeros (clipped background) gives rank-deficient — all-zero — Casorati matrices for object U while
+    the perturbed objects U +- eps2*delta2 are NOT zero there: the warm start of the perturbed SVDs (V of object U) must
+    fall back to a cold start for such patches, otherwise their singular values vanish from the risk."""
+    X, _ = synthetic_sequence(32, traj + 2, seed=5)
+    X[3:19, 8:24, :] = 0
+    fw = traj // 2
+    t = fw + 1
+    alpha, mu, sigma = 0.1, 0.05, 0.05
+    h = bridge.Handle(X, trajectory_length=traj, patch_size=patch, optimize_pgure=True, noise_alpha=alpha, noise_mu=mu,
+                      noise_sigma=sigma, random_seed=1, rank_cache=rank_cache, motion_estimation=False)
+    lams = np.array([0.5, 5.0, 40.0, 99.0])
+    vals, terms = h.probe_pgure(t, alpha, mu, sigma, lams)
+    S2 = h.probe_singular_values(t, 2)
+    h.close()
+    u = X[:, :, t - fw:t + fw + 1].astype(np.float64)
+    u /= u.max()
+    patches, _, _ = orc.arps(u, patch, t, fw, 7, traj + 2, False)
+    Pg = orc.PGUREObj(u, patches.astype(np.int64), alpha, mu, sigma, patch, 1, 1, True, True)
+    want = np.array([Pg.calc(l) for l in lams], dtype=object)
+    wv = np.array([w[0] for w in want])
+    wt = np.array([w[1] for w in want])
+    _, d2 = orc.perturbations(1, u.size)
+    o = orc.SVTObj(patches.astype(np.int64), 32, traj, patch, 1, True)
+    o.decompose(u + (d2.reshape(u.shape, order="F") * 0.01))
+    So = o.singular_values()
+    assert np.abs(S2 - So).max() / So.max() < 1e-12
+    assert np.allclose(terms, wt, rtol=1e-7, atol=1e-9)
+    assert np.abs(vals - wv).max() <= 1e-8 * np.abs(wv).max(), (vals, wv)
+
+
 @pytest.mark.parametrize("rank_cache", [0, 1, 3])
 def test_compact_cache_16x15_matches_golden_objective(golden, rank_cache):
     """The truncated factor cache on the headline shape (forced through svd_kernel=1): same objective values as the
