@@ -540,6 +540,26 @@ def test_config5_shape_pgure_small(rank_cache):
         assert st["rank_cache"] == 0
 
 
+@pytest.mark.parametrize("kw", [dict(trajectory_length=15, patch_size=8), dict(trajectory_length=15, patch_size=8, patch_overlap=3),
+                                dict(trajectory_length=31, patch_size=8, exponential_weighting=False),
+                                dict(trajectory_length=9, patch_size=6, patch_overlap=2)])
+def test_warp_svd_other_shapes_pgure(kw):
+    """64 x 15 (zero-padded column slots), overlapping patch sets, plain thresholding and a 36 x 9 shape (shared-memory
+    kernel + compact cache) through the whole PGURE pipeline against the oracle."""
+    traj = kw["trajectory_length"]
+    X, _ = synthetic_sequence(32, traj + 3, seed=21)
+    args = dict(optimize_pgure=True, lambda1=-1.0, noise_alpha=0.1, noise_mu=0.05, noise_sigma=0.05, random_seed=2, **kw)
+    t = traj // 2 + 1
+    h = bridge.Handle(X, frame_begin=t, frame_end=t + 2, **args)
+    h.process()
+    Yh, eh = h.download()
+    h.close()
+    ref, est = orc.pguresvt(X, frame_begin=t, frame_end=t + 2, **args)
+    for f in (t, t + 1):
+        assert abs(eh[f, 0] - est[f, 0]) / abs(est[f, 0]) < LAM_TOL
+        assert np.abs(Yh[:, :, f] - ref[:, :, f]).max() / np.abs(ref[:, :, f]).max() < 1e-4
+
+
 @pytest.mark.parametrize("svd_kernel", [0, 1])
 @pytest.mark.parametrize("obj", [0, 2, 3])
 def test_config5_shape_singular_values_vs_lapack(svd_kernel, obj):
