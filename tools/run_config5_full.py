@@ -10,7 +10,8 @@ import torch
 from pguresvt import _pguresvt as b
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-F = 33
+NF = int(sys.argv[3]) if len(sys.argv) > 3 else 1  # output frames (steady state: ARPS pairs and noise slices are reused)
+F = 32 + NF
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(123)
 yy, xx = torch.meshgrid(torch.arange(N, device=dev, dtype=torch.float32), torch.arange(N, device=dev, dtype=torch.float32), indexing="ij")
@@ -26,11 +27,11 @@ kw = dict(trajectory_length=31, patch_size=8, optimize_pgure=True, lambda1=-1.0,
 if len(sys.argv) > 2 and sys.argv[2] == "known":
     kw.update(noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03)
 t0 = time.time()
-h = b.Handle(X, frame_begin=16, frame_end=17, **kw)
+h = b.Handle(X, frame_begin=16, frame_end=16 + NF, **kw)
 free0, tot = torch.cuda.mem_get_info()
 t1 = time.time(); h.process(); wall = time.time() - t1
 st = h.stats()
-print("N", N, "create_s", round(t1 - t0, 2), "process_wall_s", round(wall, 2), "device_GB_in_use", round((tot - free0) / 2 ** 30, 1),
+print("N", N, "frames", NF, "create_s", round(t1 - t0, 2), "process_wall_s", round(wall, 2), "device_GB_in_use", round((tot - free0) / 2 ** 30, 1),
       {k: round(float(v), 2) for k, v in st.items()})
-Y, e = h.download(); print("lambda, alpha, mu, sigma", e[16, :], "finite", bool(np.isfinite(Y[:, :, 16]).all()),
+Y, e = h.download(); print("lambda, alpha, mu, sigma", e[16:16 + NF, :], "finite", bool(np.isfinite(Y[:, :, 16]).all()),
                            "output range", float(Y[:, :, 16].min()), float(Y[:, :, 16].max()))
