@@ -225,3 +225,44 @@ def test_odd_even_jacobi_with_tracked_norms_converges_like_lapack():
         ref = np.linalg.svd(A, compute_uv=False)
         assert np.abs(s - ref).max() <= 1e-13 * max(ref.max(), 1.0)
         assert sweeps <= 12
+
+
+def test_qform_identity_behind_the_compact_cache():
+    """The identity the truncated factor cache (compact.cuh) and k_eval3 rest on, in plain numpy: the second-difference
+    term of the risk, sum_voxels delta2 * (overlap-add of blocks / weights) (pgure.hpp:136 with svt.hpp:148-164), is linear
+    in the blocks, so for ANY threshold it equals sum_patches sum_k f_k(lambda) * q_k with q_k = u_k^T (delta2/weights)_patch v_k
+    — the perturbed objects need only their singular values and q-forms, never U and V."""
+    rng = np.random.default_rng(3)
+    N, bs, T = 12, 4, 5
+    M1 = N - bs + 1
+    # trajectories: every patch jitters by up to one pixel per slice (clamped), like ARPS output
+    base = np.array([(r, c) for c in range(M1) for r in range(M1)])
+    pos = np.stack([np.clip(base + rng.integers(-1, 2, base.shape), 0, M1 - 1) for _ in range(T)])  # (T, P, 2)
+    P = base.shape[0]
+    u = rng.random((N, N, T))
+    delta2 = np.where(rng.random((N, N, T)) < 0.72, -0.618, 1.618)
+    weights = np.zeros((N, N, T))
+    mats = np.zeros((P, bs * bs, T))
+    for p in range(P):
+        for k in range(T):
+            r, c = pos[k, p]
+            weights[r:r + bs, c:c + bs, k] += 1
+            mats[p, :, k] = u[r:r + bs, c:c + bs, k].flatten(order="F")
+    c4 = np.divide(delta2, weights, out=np.zeros_like(delta2), where=weights > 0)
+    for lam in (0.0, 0.3, 1.5):
+        direct_acc = np.zeros((N, N, T))
+        via_q = 0.0
+        for p in range(P):
+            U, S, Vt = np.linalg.svd(mats[p], full_matrices=False)
+            f = np.maximum(S - lam, 0.0)
+            block = (U * f) @ Vt
+            C = np.zeros((bs * bs, T))
+            for k in range(T):
+                r, c = pos[k, p]
+                direct_acc[r:r + bs, c:c + bs, k] += block[:, k].reshape(bs, bs, order="F")
+                C[:, k] = c4[r:r + bs, c:c + bs, k].flatten(order="F")
+            q = np.einsum("ek,ej,jk->k", U, C, Vt.T)  # q_k = u_k^T C v_k
+            via_q += float(f @ q)
+        vhat = np.divide(direct_acc, weights, out=np.zeros_like(direct_acc), where=weights > 0)
+        direct = float((delta2 * vhat).sum())
+        assert abs(direct - via_q) <= 1e-10 * max(1.0, abs(direct))
