@@ -594,8 +594,10 @@ __global__ void __launch_bounds__(128)
     k_eval_c(const double *__restrict__ S0, const double *__restrict__ S2, const double *__restrict__ S3, const double *__restrict__ Q0,
              const double *__restrict__ Q2, const double *__restrict__ Q3, const double *__restrict__ lead, int R, int m, int n, int bs,
              const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw, int only_k,
-             int want_s4, double *__restrict__ acc, double *__restrict__ partial, int *__restrict__ kpart, int *__restrict__ ovf)
+             int want_s4, double *__restrict__ acc, const double *__restrict__ accs, double *__restrict__ partial, int *__restrict__ kpart,
+             int *__restrict__ ovf)
 {
+    const double ascale = __ldg(accs);
     __shared__ __align__(16) double sv[4][EVC_RMAX * 32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = gridDim.x * 4, w = blockIdx.x * 4 + wib;
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(128)
             {
                 const int offk = __shfl_sync(0xffffffffu, myoff, k);
                 if (re && k < n && (only_k < 0 || k == only_k))
-                    atomicAdd(acc + (size_t)offk + eo + fsz * k, a[k]);
+                    acc_add(acc, (size_t)offk + eo + fsz * k, a[k], ascale);
             }
         }
     }

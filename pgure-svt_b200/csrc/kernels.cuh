@@ -46,28 +46,79 @@ __device__ __forceinline__ double to_double(T v)
     return (double)v;
 }
 
+// Overlap-add accumulators (svt.hpp:148-155) are 64-bit FIXED POINT: every contribution is rounded once to a multiple of
+// 1/scale and added as an integer, so the sum does not depend on the order the REDs land in — the reference's sequential
+// overlap-add is deterministic, and so is this one (bit-identical objective, lambda and pixels from run to run).
+// scale = 2^e is chosen per frame on the device (k_acc_scale) from the largest weight and the bound
+// |block entry| <= ||A||_F <= sqrt(m n) max|a|, so that the sum cannot overflow; for 16 x 15 patches without motion pile-up
+// e = 53, i.e. a resolution of 1.1e-16 on window-normalised values.  accs[0] = scale, accs[1] = 1/scale (exact).
+__device__ __forceinline__ void acc_add(double *acc, size_t i, double v, double scale)
+{
+    atomicAdd(reinterpret_cast<unsigned long long *>(acc) + i, (unsigned long long)__double2ll_rn(v * scale));
+}
+__device__ __forceinline__ double acc_val(const double *acc, size_t i, double inv_scale)
+{
+    return (double)reinterpret_cast<const long long *>(acc)[i] * inv_scale;
+}
+
+// largest weight of cnt[off .. off+n) -> *out (atomicMax; *out cleared by the caller)
+__global__ void k_cnt_max(const unsigned *__restrict__ cnt, size_t off, size_t n, unsigned *__restrict__ out)
+{
+    unsigned m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, cnt[off + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m)
+        atomicMax(out, m);
+}
+// accs = {2^e, 2^-e} with maxcnt * entry_bound * 2^e < 2^62
+__global__ void k_acc_scale(const unsigned *__restrict__ maxcnt, double entry_bound, double *__restrict__ accs)
+{
+    const double tot = fmax((double)*maxcnt, 1.0) * entry_bound;
+    int e = 61 - ilogb(tot);
+    e = min(max(e, -900), 60);
+    accs[0] = ldexp(1.0, e);
+    accs[1] = ldexp(1.0, -e);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // frame maxima  (u.max(), w.max(): pguresvt.hpp:116-117) — per-frame partial maxima, combined per window
 // on the host.  grid = (bpf, nframes)
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_frame_max(const T *__restrict__ X, size_t fsz, double *__restrict__ partial)
+__global__ void k_frame_max(const T *__restrict__ X, size_t fsz, double *__restrict__ partial, double *__restrict__ partial_min = nullptr)
 {
     const T *f = X + fsz * blockIdx.y;
-    double m = -INFINITY;
+    double m = -INFINITY, lo = INFINITY;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < fsz; i += (size_t)gridDim.x * blockDim.x)
-        m = fmax(m, to_double(f[i]));
+    {
+        const double v = to_double(f[i]);
+        m = fmax(m, v);
+        lo = fmin(lo, v);
+    }
     m = warp_max(m);
-    __shared__ double sm[32];
+    lo = -warp_max(-lo);
+    __shared__ double sm[2][32];
     if ((threadIdx.x & 31) == 0)
-        sm[threadIdx.x >> 5] = m;
+    {
+        sm[0][threadIdx.x >> 5] = m;
+        sm[1][threadIdx.x >> 5] = lo;
+    }
     __syncthreads();
     if (threadIdx.x < 32)
     {
-        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : -INFINITY;
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[0][threadIdx.x] : -INFINITY;
+        lo = (threadIdx.x < (blockDim.x >> 5)) ? sm[1][threadIdx.x] : INFINITY;
         m = warp_max(m);
+        lo = -warp_max(-lo);
         if (threadIdx.x == 0)
+        {
             partial[blockIdx.y * gridDim.x + blockIdx.x] = m;
+            if (partial_min) // (only the overflow bound of the fixed-point accumulators needs it: signed floating-point input)
+                partial_min[blockIdx.y * gridDim.x + blockIdx.x] = lo;
+        }
     }
 }
 
@@ -1727,8 +1778,8 @@ __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
-            double *__restrict__ acc0, double *__restrict__ partial, int *__restrict__ kpart, int qmax,
-            int *__restrict__ need_more_q)
+            double *__restrict__ acc0, const double *__restrict__ accs, double *__restrict__ partial, int *__restrict__ kpart,
+            int qmax, int *__restrict__ need_more_q)
 {
     // One PGURE evaluation for 16 x 15 patches and the three SVT objects U, U +- eps2*delta2.  16 lanes per patch; lane g
     // owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices and thresholds slot g of every object.
@@ -1748,6 +1799,7 @@ __global__ void __launch_bounds__(128, MINB)
     const int r = g & 3, c = g >> 2;
     const int fsz = N * N;
     const int base = blockIdx.x * (8 * PPG) + grp;
+    const double ascale = __ldg(accs);
 
     auto issue = [&](int j, int st) {
         int pidx = base + 8 * j;
@@ -1889,7 +1941,7 @@ __global__ void __launch_bounds__(128, MINB)
             for (int k = 0; k < SVD16_N; k++)
             {
                 const short2 p = sp[k];
-                atomicAdd(acc0 + ((p.x + r) + N * (p.y + c) + fsz * k), a0[k]);
+                acc_add(acc0, (size_t)((p.x + r) + N * (p.y + c) + fsz * k), a0[k], ascale);
             }
             s4tot += s4;
         }
@@ -1912,7 +1964,7 @@ __global__ void __launch_bounds__(128, MINB)
 // surviving leading triplets are read (S: 128 B, then 136 B per survivor instead of the whole 3,968-byte record).
 __global__ void __launch_bounds__(128)
     k_final16(const double *__restrict__ fac0, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
-              double lambda, int expw, int kref, double *__restrict__ acc)
+              double lambda, int expw, int kref, double *__restrict__ acc, const double *__restrict__ accs)
 {
     const int lane = threadIdx.x & 31, g = threadIdx.x & 15;
     int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -1936,7 +1988,7 @@ __global__ void __launch_bounds__(128)
     {
         const int id = ids ? ids[pidx] : pidx;
         const short2 p = pos[(size_t)kref * vecSize + id];
-        atomicAdd(acc + (size_t)(p.x + (g & 3)) + (size_t)N * (p.y + (g >> 2)) + (size_t)N * N * kref, a);
+        acc_add(acc, (size_t)(p.x + (g & 3)) + (size_t)N * (p.y + (g >> 2)) + (size_t)N * N * kref, a, __ldg(accs));
     }
 }
 
@@ -1945,13 +1997,15 @@ __global__ void __launch_bounds__(128)
 // per-CTA s4 partials of k_eval3 are folded in (third sum) so that one fixed-order reduction finishes all three.
 // partial: gridDim.x * 4 doubles (s1, s5, s4, triplets streamed)
 __global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
-                            const double *__restrict__ s4part, const int *__restrict__ kpart, int ns4, double *__restrict__ partial)
+                            const double *__restrict__ accs, const double *__restrict__ s4part, const int *__restrict__ kpart, int ns4,
+                            double *__restrict__ partial)
 {
     double s1 = 0, s5 = 0, s4 = 0, sk = 0;
+    const double ainv = __ldg(accs + 1);
     // (an unrolled variant with more loads in flight per thread needs 58 registers, halves the resident CTAs and is slower)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
-        const double v0 = norm_or_zero(acc0[i], cnt[i]);
+        const double v0 = norm_or_zero(acc_val(acc0, i, ainv), cnt[i]);
         acc0[i] = 0.0;
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
@@ -2001,9 +2055,10 @@ __global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__
 template <int NMAX>
 __global__ void k_recon(const double *__restrict__ fac, size_t rec, int m, int n, int ldv, int bs,
                         const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
-                        double lambda, int expw, int only_k, double *__restrict__ acc, int G)
+                        double lambda, int expw, int only_k, double *__restrict__ acc, const double *__restrict__ accs, int G)
 {
     extern __shared__ double smr[];
+    const double ascale = __ldg(accs);
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G, g = threadIdx.x % G;
     const int pidx = blockIdx.x * gpb + gl;
@@ -2067,7 +2122,7 @@ __global__ void k_recon(const double *__restrict__ fac, size_t rec, int m, int n
             if (k < n && (only_k < 0 || k == only_k))
             {
                 const short2 p = sp[k];
-                atomicAdd(acc + (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k, a[k]);
+                acc_add(acc, (size_t)(p.x + r) + (size_t)N * (p.y + c) + fsz * k, a[k], ascale);
             }
     }
 }
@@ -2080,23 +2135,24 @@ __global__ void k_recon(const double *__restrict__ fac, size_t rec, int m, int n
 
 __global__ void k_risk(const double *__restrict__ u, const int8_t *__restrict__ d1, const int8_t *__restrict__ d2neg,
                        const unsigned *__restrict__ cnt, const double *__restrict__ acc0, const double *__restrict__ acc1,
-                       const double *__restrict__ acc2p, const double *__restrict__ acc2m, size_t tot, double alpha,
-                       double mu, double sigmasq, double dNeg, double dPos, double *__restrict__ partial)
+                       const double *__restrict__ acc2p, const double *__restrict__ acc2m, const double *__restrict__ accs, size_t tot,
+                       double alpha, double mu, double sigmasq, double dNeg, double dPos, double *__restrict__ partial)
 {
     double s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+    const double ainv = __ldg(accs + 1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
         const unsigned c = cnt[i];
         const double U = u[i];
-        const double v0 = norm_or_zero(acc0[i], c);
-        const double v2p = norm_or_zero(acc2p[i], c);
-        const double v2m = norm_or_zero(acc2m[i], c);
+        const double v0 = norm_or_zero(acc_val(acc0, i, ainv), c);
+        const double v2p = norm_or_zero(acc_val(acc2p, i, ainv), c);
+        const double v2m = norm_or_zero(acc_val(acc2m, i, ainv), c);
         const double d = fabs(v0 - U);
         s1 += d * d;
         s2 += U;
         if (acc1)
         {
-            const double v1 = norm_or_zero(acc1[i], c);
+            const double v1 = norm_or_zero(acc_val(acc1, i, ainv), c);
             s3 += ((double)d1[i] * (alpha * U - alpha * mu + sigmasq)) * (v1 - v0);
         }
         s4 += (d2neg[i] ? dNeg : dPos) * (v2p - 2 * v0 + v2m);
@@ -2171,11 +2227,12 @@ __global__ void k_sum(const double *__restrict__ x, size_t n, double *__restrict
 
 // v = acc / weights, non-finite -> 0, times scale (svt.hpp:163-164, pguresvt.hpp:147); n voxels starting at
 // offset `off` of acc/cnt, written to out[0..n)
-__global__ void k_finalize(const double *__restrict__ acc, const unsigned *__restrict__ cnt, size_t off, size_t n,
-                           double scale, double *__restrict__ out)
+__global__ void k_finalize(const double *__restrict__ acc, const double *__restrict__ accs, const unsigned *__restrict__ cnt, size_t off,
+                           size_t n, double scale, double *__restrict__ out)
 {
+    const double ainv = __ldg(accs + 1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = norm_or_zero(acc[off + i], cnt[off + i]) * scale;
+        out[i] = norm_or_zero(acc_val(acc, off + i, ainv), cnt[off + i]) * scale;
 }
 
 } // namespace pgs

@@ -94,6 +94,7 @@ struct pguresvt_handle
     int arps_ring = 0;
     int *dIds = nullptr;
     unsigned *dCnt = nullptr;
+    double *dAccScale = nullptr; // {2^e, 2^-e} of the fixed-point overlap-add accumulators (k_acc_scale), + the largest weight
     double *dAcc[4] = {nullptr, nullptr, nullptr, nullptr};
     double *dFac[4] = {nullptr, nullptr, nullptr, nullptr};
     int8_t *dD1 = nullptr, *dD2 = nullptr;
@@ -126,14 +127,14 @@ struct pguresvt_handle
     long long noise_launches = 0;
     std::string noise_err;
 
-    std::vector<double> xmax, zmax; // per resident frame
+    std::vector<double> xmax, zmax, xmin; // per resident frame
     std::vector<double> est;        // (fe-fb) x 4 row-per-quantity
     bool uploaded = false, prefiltered = false, perturbed = false, attr_warm = false, attr_qform = false, acc0_clean = false;
     int q_k = 0;           // number of leading triplets whose q-forms exist for the current frame
     int *dNeedQ = nullptr; // set by k_eval3 when a triplet beyond q_k survives
     int *dKpart = nullptr; // per-warp count of singular triplets streamed by k_eval3
     long long cur_t = -1;
-    double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0;
+    double cur_uMax = 0, cur_wMax = 0, cur_sumU = 0, cur_absmax = 1.0; // cur_absmax: max |u| of the normalised window
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
     double stats[PGS_NSTATS] = {0};
     long long launches = 0;
@@ -182,7 +183,7 @@ static void free_all(pguresvt_handle *h)
         F(h->dAcc[i]), F(h->dFac[i]);
     for (int i = 0; i < 4; i++)
         F(h->dSc[i]), F(h->dQc[i]);
-    F(h->dLead), F(h->dOvf), F(h->dFacScratch), F(h->dUn);
+    F(h->dLead), F(h->dOvf), F(h->dFacScratch), F(h->dUn), F(h->dAccScale);
     if (h->hOvf)
         cudaFreeHost(h->hOvf);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
@@ -319,6 +320,8 @@ static int create_impl(pguresvt_handle *h)
     CU(cudaMalloc(&h->dIds, (size_t)h->P * sizeof(int)));
     CU(cudaMemcpy(h->dIds, ids.data(), (size_t)h->P * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->dCnt, wtot * sizeof(unsigned)));
+    CU(cudaMalloc(&h->dAccScale, 4 * sizeof(double)));
+    CU(cudaMemset(h->dAccScale, 0, 4 * sizeof(double)));
     for (int k = 0; k < h->nobj; k++)
     {
         const int o = h->objs[k];
@@ -358,7 +361,7 @@ static int create_impl(pguresvt_handle *h)
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
     CU(cudaMemset(h->dOut, 0, 16 * sizeof(double)));
     h->dNeedQ = reinterpret_cast<int *>(h->dOut + 4); // travels home with the four sums of objective_fused
-    CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * sizeof(double)));
+    CU(cudaMalloc(&h->dMaxPartial, (size_t)nres * 64 * 2 * sizeof(double)));
     CU(cudaMalloc(&h->dY, h->fsz * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dEst, (size_t)4 * nblk * sizeof(double)));
     CU(cudaMalloc(&h->dSweeps, 4 * sizeof(int)));
@@ -387,6 +390,7 @@ static int create_impl(pguresvt_handle *h)
         CU(cudaMalloc(&h->dLead, per_rank * h->Rc));
     }
     h->xmax.assign(nres, 0.0);
+    h->xmin.assign(nres, 0.0);
     h->zmax.assign(nres, 0.0);
     h->est.assign((size_t)4 * nblk, 0.0);
     return PGS_OK;
@@ -479,13 +483,16 @@ static int prefilter_t(pguresvt_handle *h)
     const uint32_t nres = h->r1 - h->r0;
     const size_t ntot = h->fsz * nres;
     const int bpf = 64;
-    std::vector<double> part((size_t)nres * bpf);
-    k_frame_max<T><<<dim3(bpf, nres), 256, 0, h->st>>>((const T *)h->dX, h->fsz, h->dMaxPartial);
+    std::vector<double> part((size_t)nres * bpf * 2);
+    k_frame_max<T><<<dim3(bpf, nres), 256, 0, h->st>>>((const T *)h->dX, h->fsz, h->dMaxPartial, h->dMaxPartial + (size_t)nres * bpf);
     LAUNCHED(h);
     CU(cudaMemcpyAsync(part.data(), h->dMaxPartial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     for (uint32_t f = 0; f < nres; f++)
+    {
         h->xmax[f] = *std::max_element(part.begin() + (size_t)f * bpf, part.begin() + (size_t)(f + 1) * bpf);
+        h->xmin[f] = *std::min_element(part.begin() + (size_t)(nres + f) * bpf, part.begin() + (size_t)(nres + f + 1) * bpf);
+    }
     if (h->p.median_size > 0)
     {
         const uint16_t *src16;
@@ -651,6 +658,13 @@ static int stage_window(pguresvt_handle *h, uint32_t t)
     const uint32_t la = a - h->r0;
     h->cur_uMax = uMax;
     h->cur_wMax = wMax;
+    {
+        double lo = h->xmin[la];
+        for (uint32_t k = 1; k < h->win; k++)
+            lo = std::min(lo, h->xmin[la + k]);
+        const double am = std::fabs(lo / uMax);
+        h->cur_absmax = std::isfinite(am) ? std::max(1.0, am) : 1.0;
+    }
     const size_t off = h->fsz * la;
     switch (h->dtype)
     {
@@ -993,6 +1007,16 @@ static int stage_count(pguresvt_handle *h, int only_k)
     k_count<<<cdiv(nt, 256), 256, 0, h->st>>>(h->dPos, h->dIds, h->P, h->vecSize, h->N, h->p.block_size, h->win, only_k,
                                               h->dCnt);
     LAUNCHED(h);
+    { // scale of the fixed-point accumulators: |block entry| <= ||A||_F <= sqrt(m n) max|a| (perturbed objects: + eps2 |delta2|)
+        unsigned *dMaxCnt = reinterpret_cast<unsigned *>(h->dAccScale + 2);
+        CU(cudaMemsetAsync(dMaxCnt, 0, sizeof(unsigned), h->st));
+        const size_t off = only_k >= 0 ? h->fsz * only_k : 0, nv = only_k >= 0 ? h->fsz : wtot;
+        k_cnt_max<<<std::min(cdiv(nv, 1024), h->sm_count * 8), 256, 0, h->st>>>(h->dCnt, off, nv, dMaxCnt);
+        LAUNCHED(h);
+        const double amax = std::max(1.0, h->cur_absmax) + 0.02;
+        k_acc_scale<<<1, 1, 0, h->st>>>(dMaxCnt, std::sqrt((double)h->m * h->n) * amax, h->dAccScale);
+        LAUNCHED(h);
+    }
     CU(cudaGetLastError());
     return PGS_OK;
 }
@@ -1005,10 +1029,10 @@ static int launch_recon_generic(pguresvt_handle *h, const double *fac, const int
     const size_t smem = ((size_t)h->ldv * h->n + 2 * NMAX) * sizeof(double) * gpb;
     if (NMAX == 16)
         k_recon<16><<<cdiv(np, gpb), threads, smem, h->st>>>(fac, h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos, ids, np, h->vecSize,
-                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, G);
+                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, h->dAccScale, G);
     else
         k_recon<32><<<cdiv(np, gpb), threads, smem, h->st>>>(fac, h->rec, h->m, h->n, h->ldv, h->p.block_size, h->dPos, ids, np, h->vecSize,
-                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, G);
+                                                             h->N, lambda, h->p.exp_weighting, only_k, acc, h->dAccScale, G);
     LAUNCHED(h);
     CU(cudaGetLastError());
     return PGS_OK;
@@ -1023,7 +1047,7 @@ static int compact_accumulate(pguresvt_handle *h, double lambda, int only_k, int
     CU(cudaMemsetAsync(h->dOvf, 0, sizeof(int), h->st));
     k_eval_c<<<h->evc_warps / 4, 128, 0, h->st>>>(h->dSc[0], h->dSc[2], h->dSc[3], h->dQc[0], h->dQc[2], h->dQc[3], h->dLead, h->Rc, h->m, h->n,
                                                    h->p.block_size, h->dPos, h->dIds, h->P, h->vecSize, h->N, lambda, h->p.exp_weighting, only_k,
-                                                   want_s4, h->dAcc[0], h->dPartialE, h->dKpart, h->dOvf);
+                                                   want_s4, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->dOvf);
     LAUNCHED(h);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->hOvf, h->dOvf, sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -1068,7 +1092,8 @@ static int objective_compact(pguresvt_handle *h, double lambda, double alpha, do
     int rc = compact_accumulate(h, lambda, -1, 1);
     if (rc)
         return rc;
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, h->evc_warps, h->dPartial);
+    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart, h->evc_warps,
+                                                h->dPartial);
     LAUNCHED(h);
     k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
     LAUNCHED(h);
@@ -1111,7 +1136,7 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
     if (h->use_l4 && obj == 0 && only_k >= 0)
     { // output slice of the register-SVD configuration: rank-adaptive single-slice kernel
         k_final16<<<cdiv((long long)h->P * 16, 128), 128, 0, h->st>>>(h->dFac[0], h->dPos, h->P == h->vecSize ? nullptr : h->dIds, h->P,
-                                                                      h->vecSize, h->N, lambda, h->p.exp_weighting, only_k, h->dAcc[0]);
+                                                                      h->vecSize, h->N, lambda, h->p.exp_weighting, only_k, h->dAcc[0], h->dAccScale);
         LAUNCHED(h);
         CU(cudaGetLastError());
         return PGS_OK;
@@ -1136,10 +1161,10 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
         const int ppg_eff = (ppg == 1 || ppg == 4 || ppg == 16 || ppg == 32) ? ppg : 8;
         kev<<<cdiv(h->P, 8 * ppg_eff), 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos,
                                                         h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
-                                                        h->p.exp_weighting, h->dAcc[0], h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
+                                                        h->p.exp_weighting, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
         LAUNCHED(h);
-        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dPartialE, h->dKpart, 4 * cdiv(h->P, 8 * ppg_eff),
-                                                    h->dPartial);
+        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
+                                                    4 * cdiv(h->P, 8 * ppg_eff), h->dPartial);
         LAUNCHED(h);
         k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
         LAUNCHED(h);
@@ -1182,7 +1207,7 @@ static int objective(pguresvt_handle *h, double lambda, double alpha, double mu,
     }
     const size_t wtot = h->fsz * h->win;
     const double sigmasq = sigma * sigma;
-    k_risk<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dD1, h->dD2, h->dCnt, h->dAcc[0], h->dAcc[1], h->dAcc[2], h->dAcc[3], wtot,
+    k_risk<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dD1, h->dD2, h->dCnt, h->dAcc[0], h->dAcc[1], h->dAcc[2], h->dAcc[3], h->dAccScale, wtot,
                                            alpha, mu, sigmasq, h->d2Neg, h->d2Pos, h->dPartial);
     LAUNCHED(h);
     k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 5, h->dOut);
@@ -1420,7 +1445,7 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
         if ((rc = launch_recon(h, 0, lambda, h->cur_sl)))
             return rc;
         const uint32_t lt = t - h->fb;
-        k_finalize<<<std::min(cdiv(h->fsz, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dCnt, h->fsz * h->cur_sl, h->fsz,
+        k_finalize<<<std::min(cdiv(h->fsz, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dAccScale, h->dCnt, h->fsz * h->cur_sl, h->fsz,
                                                                                     h->cur_uMax, h->dY + h->fsz * lt);
         LAUNCHED(h);
         const uint32_t nblk = h->fe - h->fb;
@@ -1663,7 +1688,7 @@ extern "C" int pguresvt_probe_reconstruct(pguresvt_handle *h, uint32_t t, double
         return rc;
     if (!h->dV)
         CU(cudaMalloc(&h->dV, wtot * sizeof(double)));
-    k_finalize<<<std::min(cdiv(wtot, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dCnt, 0, wtot, 1.0, h->dV);
+    k_finalize<<<std::min(cdiv(wtot, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dAccScale, h->dCnt, 0, wtot, 1.0, h->dV);
     LAUNCHED(h);
     CU(cudaMemcpyAsync(v, h->dV, wtot * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
