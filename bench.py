@@ -1,17 +1,30 @@
 #!/usr/bin/env python
 """bench.py — denoised frames/s of the PGURE-SVT hot path (BASELINE.json metric) on N B200s of one node.
 
-Workload (BASELINE.json configs[3]): synthetic Poisson-Gaussian 1024x1024x1000 uint16 sequence, patch 4,
-trajectory 15, per-frame PGURE lambda search (tol 1e-7, max_iter 500), ARPS on, median radius 5.
-A *step* is one pass of the hot path over one contiguous block of `--frames-per-step` frames of that sequence
-(plus the 7 halo frames each side the windows need) on every rank — exactly the unit of frame sharding
-(src/utils.hpp:150-166).  Each rank works on its own block (weak scaling), then the denoised frames are
-all-gathered over NCCL.  `value` = frames all ranks denoised / max-over-ranks time with the block resident in
-HBM; `e2e` = the same through the C ABI with pinned HOST buffers (H2D of block+halo, D2H of the denoised
-frames inside the timed region).
+Workloads (BASELINE.json `configs`, chosen with --config; the default 4 is the one the metric is quoted on):
+  3  synthetic Poisson-Gaussian 512x512x200 uint16, patch 4, trajectory 15, FIXED lambda (pure SVT path)
+  4  synthetic 1024x1024x1000 uint16, patch 4, trajectory 15, per-frame PGURE lambda search (tol 1e-7, max_iter 500)
+  5  synthetic 4096x4096x500 uint16, patch 8, trajectory 31 (64x31 Casorati), PGURE lambda + ARPS
+all with ARPS on, median radius 5 and (PGURE) the noise parameters estimated per frame.
 
-`--impl reference` times the CPU path instead (the restated oracle — the upstream binary cannot be built in
-this image: Armadillo/NLopt/libtiff absent) on all host cores, on a bounded crop of the same workload.
+A *step* is one pass of the hot path over one contiguous block of `--frames-per-step` frames per GPU (plus the halo
+frames the windows need) — exactly the unit of frame sharding (src/utils.hpp:150-166).
+
+  value  one process per GPU (the driver's torchrun launch), each rank's block resident in HBM when the timed region starts,
+         handle API, the denoised frames all-gathered over NCCL; frames all ranks denoised / max-over-ranks time.
+  e2e    the drop-in call a user makes: `pguresvt_u16(X)` (the role of the reference's Cython entry, _pguresvt.pyx:240) on a
+         pageable numpy sequence of frames-per-step x N frames, returning a fresh numpy array — host->device and device->host
+         copies, allocation and the product's own multi-GPU fan-out (pguresvt_params.n_gpus = N: one host thread + handle
+         per device inside the call) all inside the timed region.  Under torchrun rank 0 makes that one call and drives all
+         N devices; the other ranks wait on a host-side (gloo) barrier.  Config 5 (11 s per frame) times the handle API with
+         pinned host buffers and streamed output instead (a one-shot call denoises every frame of the sequence it is given,
+         and a 31-frame window is the shortest sequence).
+  parity (N = 1) the same crop the CPU leg runs goes through the GPU path: max relative pixel / lambda / noise-estimate
+         error and the number of ARPS trajectory mismatches against the oracle — BASELINE.md §5's columns.
+
+`--impl reference` times the CPU path instead (the restated oracle — the upstream binary cannot be built in this image:
+Armadillo/NLopt/libtiff absent) on all host cores, on a bounded crop of the same workload; the frames/s it reports are
+EXTRAPOLATED to the full frame size by area.
 """
 import argparse
 import ctypes as C
@@ -29,26 +42,25 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "pgure-svt_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_FRAMES_TOTAL = 1000
-FW = 7
+CONFIGS = {
+    3: dict(size=512, frames=200, patch=4, traj=15, pgure=False, fps_step=32, crop=256,
+            name="configs[2]: synthetic Poisson-Gaussian 512x512x200 uint16, patch 4, trajectory 15, fixed lambda 0.15 (pure SVT path)"),
+    4: dict(size=1024, frames=1000, patch=4, traj=15, pgure=True, fps_step=32, crop=128,
+            name="configs[3]: synthetic Poisson-Gaussian 1024x1024x1000 uint16, patch 4, trajectory 15, per-frame PGURE lambda search (tol 1e-7)"),
+    5: dict(size=4096, frames=500, patch=8, traj=31, pgure=True, fps_step=1, crop=64,
+            name="configs[4]: synthetic Poisson-Gaussian 4096x4096x500 uint16, patch 8, trajectory 31 (64x31 Casorati), PGURE lambda + ARPS"),
+}
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm, src = 6650.0, "fallback"
+    hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(p):
         try:
-            hbm, src = float(json.load(open(p))["hbm_gbs"]), "measured"
+            hbm, src = float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    fp64, fsrc = 37.0, "nominal"
-    q = os.path.join(ROOT, "profiles", "fp64_peak.json")
-    if os.path.exists(q):
-        try:
-            fp64, fsrc = float(json.load(open(q))["dfma_tflops"]), "measured (profiles/fp64_peak.json)"
-        except Exception:
-            pass
-    return hbm, src, fp64, fsrc
+    return hbm, src
 
 
 def make_block(size, nfr, seed, alpha=0.1, mu=0.1, sigma=0.1):
@@ -86,32 +98,66 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference(args, size, kw_orc, crop=128):
-    """Oracle on all host cores over a bounded sample: one frame per core of a crop x crop cut of the same data."""
+def cpu_reference(cfg, size, kw_orc, crop):
+    """Oracle on all host cores over a bounded sample: one frame per core of a crop x crop cut of the same data.
+    Returns (cpu_baseline dict, wall seconds, (X, fb, fe, Y, est) of the sample for the parity leg)."""
     from oracle import orc
 
+    fw = cfg["traj"] // 2
     cores = os.cpu_count() or 1
-    nfr = max(2 * FW + 1, cores + 2 * FW)
+    nfr = cores + 2 * fw
     X = make_block(crop, nfr, seed=123)
-    fb, fe = FW, FW + cores
-    orc.pguresvt(X[:, :, : 2 * FW + 1], n_jobs=1, frame_begin=FW, frame_end=FW + 1, **{**kw_orc, "max_iter": 3})  # warm
+    fb, fe = fw, fw + cores
+    orc.pguresvt(X[:, :, : 2 * fw + 1], n_jobs=1, frame_begin=fw, frame_end=fw + 1, **{**kw_orc, "max_iter": 3})  # warm
     orc.stage_times(reset=True)
     t0 = time.perf_counter()
-    orc.pguresvt(X, n_jobs=cores, frame_begin=fb, frame_end=fe, **kw_orc)
+    Y, est = orc.pguresvt(X, n_jobs=cores, frame_begin=fb, frame_end=fe, **kw_orc)
     dt = time.perf_counter() - t0
     st = orc.stage_times(reset=True)
     scale = (crop * crop) / float(size * size)
     fps = (fe - fb) / dt * scale
     nobj = 4 if kw_orc.get("optimize_pgure", True) else 1
-    svds = (crop - 3) ** 2 * nobj * (fe - fb)
+    svds = (crop - cfg["patch"] + 1) ** 2 * nobj * (fe - fb)
     return {
         "value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
         "sample": f"{fe - fb} frames (one per core) of a {crop}x{crop} crop of the same synthetic sequence, full pipeline; "
-                  f"frames/s scaled by {crop}^2/{size}^2; restated oracle (reference structure: per-patch LAPACK dgesdd, "
-                  f"std::thread frame fan-out), not the upstream binary",
+                  f"frames/s EXTRAPOLATED to {size}x{size} by area ({crop}^2/{size}^2); restated oracle (reference structure: "
+                  f"per-patch LAPACK dgesdd, std::thread frame fan-out), not the upstream binary",
         "wall_s": dt, "patch_svds_per_s": svds / (st["svd"] / cores) if st["svd"] > 0 else None,
         "svd_backend": orc.svd_backend(),
-    }, dt
+    }, dt, (X, fb, fe, Y, est)
+
+
+def parity_leg(cfg, kw, sample, device):
+    """GPU path on the CPU leg's sample against the oracle's outputs (BASELINE.md §5 columns)."""
+    from oracle import orc
+    from pguresvt import _pguresvt as bridge
+
+    X, fb, fe, Yo, eo = sample
+    fw = cfg["traj"] // 2
+    h = bridge.Handle(X, frame_begin=fb, frame_end=fe, device=device, **kw)
+    h.process()
+    Y, e = h.download()
+    pix = max(np.abs(Y[:, :, t] - Yo[:, :, t]).max() / np.abs(Yo[:, :, t]).max() for t in range(fb, fe))
+    out = {"frames": fe - fb, "frame_size": X.shape[0], "max_rel_pixel_err": float(pix)}
+    if kw.get("optimize_pgure", True):
+        lam = np.abs(e[fb:fe, 0] - eo[fb:fe, 0]) / np.abs(eo[fb:fe, 0])
+        out["max_rel_lambda_err"] = float(lam.max())
+        out["noise_rel_err"] = float((np.abs(e[fb:fe, 1:] - eo[fb:fe, 1:]) / np.abs(eo[fb:fe, 1:])).max())
+        # pixels at the ORACLE's lambda (separates the reconstruction from the end point of the search)
+        t = fb
+        v = h.probe_reconstruct(t, float(eo[t, 0]))
+        umax = X[:, :, t - fw:t + fw + 1].max()
+        out["max_rel_pixel_err_at_oracle_lambda"] = float(np.abs(v[:, :, fw] * umax - Yo[:, :, t]).max() / np.abs(Yo[:, :, t]).max())
+    # ARPS trajectories of the first sampled frame, bit for bit
+    t = fb
+    Z = np.stack([orc.median_u16(X[:, :, i], 5) for i in range(t - fw, t + fw + 1)], axis=2).astype(np.float64)
+    want, _, _ = orc.arps(Z / Z.max(), cfg["patch"], t, fw, 7, X.shape[2], True)
+    got = h.probe_arps(t)
+    out["arps_mismatches"] = int((got != want.astype(np.int32)).sum())
+    out["arps_entries_compared"] = int(got.size)
+    h.close()
+    return out
 
 
 def main():
@@ -120,16 +166,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--frames-per-step", type=int, default=32,
-                    help="frames of the 1000-frame sequence each GPU denoises per step (plus 7 halo frames each side).  Every step "
-                         "starts cold (halo medians, cold ARPS pairs, cold noise window — what a GPU pays once per job); measured: "
-                         "125-frame steps (1000 frames / 8 GPUs) give the same 23.6 frames/s as 32-frame steps, which keep a step at ~1.4 s")
+    ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5], help="BASELINE.json workload (see the module docstring)")
+    ap.add_argument("--size", type=int, default=None, help="override the frame size of the chosen config (tests)")
+    ap.add_argument("--frames-per-step", type=int, default=None,
+                    help="frames of the sequence each GPU denoises per step (plus halo frames each side).  Every step starts cold "
+                         "(halo medians, cold ARPS pairs, cold noise window — what a GPU pays once per job); measured: 125-frame steps "
+                         "(1000 frames / 8 GPUs) give the same frames/s as 32-frame steps, which keep a step at ~1.4 s")
     ap.add_argument("--noise", default="estimate", choices=["known", "estimate"],
                     help="estimate: alpha/mu/sigma unknown, estimated per frame on the GPU (the reference's default usage); "
                          "known: alpha/mu/sigma supplied (isolates SVD + lambda search)")
-    ap.add_argument("--fixed-lambda", action="store_true", help="configs[2]-style pure SVT path (no PGURE search)")
+    ap.add_argument("--fixed-lambda", action="store_true", help="same as --config 3 but at the size of the chosen config")
+    ap.add_argument("--eps1-mode", type=int, default=0, choices=[0, 1],
+                    help="0: PGURE as the reference computes it (eps1*delta1 integer-truncated, 3 SVT objects; DESIGN Q26); "
+                         "1: the intended first-order perturbation (4 SVT objects, generic evaluation path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-oneshot", action="store_true", help="time e2e through the handle API (as config 5 does)")
     args = ap.parse_args()
 
     # libraries (NCCL prints its version banner on stdout) must not pollute the ONE JSON line: everything written to fd 1
@@ -145,31 +196,41 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    size, fps_step = args.size, args.frames_per_step
+    cfg = dict(CONFIGS[args.config])
+    if args.fixed_lambda:
+        cfg["pgure"] = False
+    size = args.size or cfg["size"]
+    fps_step = args.frames_per_step or cfg["fps_step"]
+    n_total, fw = cfg["frames"], cfg["traj"] // 2
+    pgure = cfg["pgure"]
 
     estimate = args.noise == "estimate"
-    kw = dict(trajectory_length=15, patch_size=4, patch_overlap=1, motion_window=7, motion_filter=5, noise_method=4,
-              max_iter=500, random_seed=1, exponential_weighting=True, motion_estimation=True, tol=1e-7)
-    if args.fixed_lambda:
+    kw = dict(trajectory_length=cfg["traj"], patch_size=cfg["patch"], patch_overlap=1, motion_window=7, motion_filter=5,
+              noise_method=4, max_iter=500, random_seed=1, exponential_weighting=True, motion_estimation=True, tol=1e-7)
+    if not pgure:
         kw.update(optimize_pgure=False, lambda1=0.15)
     else:
         kw.update(optimize_pgure=True, lambda1=-1.0)
         if not estimate:
             # known noise in window-normalised units: alpha = mu = sigma = 0.1 of the clean scale
             kw.update(noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03)
-    workload = (f"synthetic Poisson-Gaussian {size}x{size}x{N_FRAMES_TOTAL} uint16, patch 4, trajectory 15, "
-                + ("fixed lambda 0.15" if args.fixed_lambda else "per-frame PGURE lambda search (tol 1e-7)")
-                + f", ARPS on, median radius 5, noise {'estimated per frame' if estimate else 'known'}; step = block of "
-                f"{fps_step} frames (+{FW} halo frames each side) per GPU")
+    workload = (cfg["name"] + (f" [frame size overridden: {size}]" if size != cfg["size"] else "")
+                + (" [fixed lambda 0.15]" if args.fixed_lambda else "")
+                + f", ARPS on, median radius 5" + (f", noise {'estimated per frame' if estimate else 'known'}" if pgure else "")
+                + (f", eps1_mode {args.eps1_mode}" if pgure else "")
+                + f"; step = block of {fps_step} frames (+{fw} halo frames each side) per GPU")
     config = {"workload": workload, "frames_per_step_per_gpu": fps_step, "frame_size": size, "sharding": "frames",
               "l2_policy": "inputs larger than L2: each frame touches >= 4 GB of SVD factors (126 MB L2)"}
+    metric = {3: "denoised frames/s (512^2, fixed lambda)", 4: "denoised frames/s (1024^2, PGURE lambda)",
+              5: "denoised frames/s (4096^2, 64x31, PGURE lambda + ARPS)"}[args.config]
+    if args.fixed_lambda and args.config != 3:
+        metric = "denoised frames/s (fixed lambda)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        kw_orc = {k: v for k, v in kw.items()}
-        cb, dt = cpu_reference(args, size, kw_orc)
-        line = {"metric": "denoised frames/s (1024^2, PGURE lambda)", "value": cb["value"], "unit": "frames/s",
+        cb, dt, _ = cpu_reference(cfg, size, dict(kw), cfg["crop"])
+        line = {"metric": metric, "value": cb["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "impl": "reference", "cpu_baseline": cb,
@@ -181,35 +242,40 @@ def main():
     from pguresvt import _pguresvt as bridge
 
     torch.cuda.set_device(local_rank)
-    dist = None
+    dist, host_group = None, None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # host-side barrier for the leg in which rank 0 drives every device
+
+    L = bridge.load()
+    # FP64 roofline denominator, measured in this job (rank 0's device, before anything else runs on it)
+    dfma = {"burst": None, "sustained": None}
+    if rank == 0:
+        b, s = C.c_double(0), C.c_double(0)
+        if L.pguresvt_bench_dfma(local_rank, C.byref(b), C.byref(s)) == 0:
+            dfma = {"burst": b.value, "sustained": s.value}
+    if world > 1:
+        dist.barrier()
 
     # this rank's block of the long sequence (middle of the sequence → regular windows)
-    if world * fps_step > N_FRAMES_TOTAL:
-        raise SystemExit(f"--frames-per-step {fps_step} x {world} GPUs exceeds the {N_FRAMES_TOTAL}-frame sequence")
-    # contiguous blocks centred in the sequence; 8 x 125 tiles it exactly (edge ranks then apply the first/last-window rules)
-    fb = (N_FRAMES_TOTAL - world * fps_step) // 2 + rank * fps_step
+    if world * fps_step > n_total:
+        raise SystemExit(f"--frames-per-step {fps_step} x {world} GPUs exceeds the {n_total}-frame sequence")
+    # contiguous blocks centred in the sequence; 8 x 125 tiles config 4 exactly (edge ranks then apply the first/last-window rules)
+    fb = (n_total - world * fps_step) // 2 + rank * fps_step
     fe = fb + fps_step
     kwh = dict(kw)
-    kwh["device"] = local_rank
-    h = bridge.Handle(shape=(size, size, N_FRAMES_TOTAL), dtype=np.uint16, frame_begin=fb, frame_end=fe, **kwh)
+    kwh.update(device=local_rank, eps1_mode=args.eps1_mode, n_gpus=1)
+    h = bridge.Handle(shape=(size, size, n_total), dtype=np.uint16, frame_begin=fb, frame_end=fe, **kwh)
     r0, r1 = h.resident_range()
     nres = r1 - r0
     Xb = make_block(size, nres, seed=123 + rank)  # (size, size, nres) F-order == frames contiguous
     fsz = size * size
     nbytes_in = fsz * nres * 2
-    # pinned host buffers for the end-to-end leg
     hin = torch.empty(nbytes_in, dtype=torch.uint8, pin_memory=True)
     hin.numpy()[:] = np.frombuffer(Xb.tobytes(order="F"), dtype=np.uint8)
-    hout = torch.empty(fsz * fps_step, dtype=torch.float64, pin_memory=True)
-    hest = np.zeros((N_FRAMES_TOTAL, 4), dtype=np.float64, order="F")
     din = hin.cuda()  # block resident in HBM for the `value` leg
-    L = bridge.load()
-    cudart = C.CDLL("libcudart.so") if False else None  # noqa: F841  (all copies go through the C ABI)
-
     ybytes = fsz * fps_step * 8
 
     class _Arr:
@@ -224,17 +290,6 @@ def main():
         h.process()
         if world > 1:
             dist.all_gather_into_tensor(gathered, yblock)
-
-    fake_base = hin.data_ptr() - fsz * r0 * 2
-    yfake = hout.data_ptr() - fsz * fb * 8
-
-    def step_e2e():
-        bridge.check(L.pguresvt_upload(h.h, C.c_void_p(fake_base)), "upload")
-        h.process()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, yblock)
-        bridge.check(L.pguresvt_download(h.h, C.cast(C.c_void_p(yfake), C.POINTER(C.c_double)),
-                                         hest.ctypes.data_as(C.POINTER(C.c_double))), "download")
 
     def barrier():
         if world > 1:
@@ -259,7 +314,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # accumulate per-stage device time over the timed steps
     acc = {}
     nst = {"n": 0}
 
@@ -271,14 +325,67 @@ def main():
         nst["n"] += 1
 
     dt = timed(step_resident_stats, args.steps)
-    for _ in range(1):
+
+    # ---------------------------------------------------------------- end-to-end leg
+    oneshot = args.config != 5 and not args.no_e2e_oneshot
+    e2e_extra = {}
+    if oneshot:
+        # rank 0 makes ONE drop-in call per step over fps_step x world frames and the call fans out over the `world` devices
+        # itself; the other ranks keep out of the way on a host-side barrier (their handles stay allocated, their GPUs idle)
+        nfr_e2e = fps_step * world
+        kwo = dict(kw)
+        kwo.update(device=0, eps1_mode=args.eps1_mode, n_gpus=world)
+        h2d, d2h = fsz * 2 * nfr_e2e, fsz * 8 * nfr_e2e + 32 * nfr_e2e
+        dt_e2e = 0.0
+        if rank == 0:
+            Xe = make_block(size, nfr_e2e, seed=77)  # pageable numpy, F-order
+            bridge.pguresvt_u16(Xe, **kwo)  # warm-up (contexts on every device, page-locked staging)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                Ye, ee, _ = bridge.pguresvt_u16(Xe, **kwo)
+            dt_e2e = time.perf_counter() - t0
+            e2e_extra["api"] = f"pguresvt_u16(X[{size},{size},{nfr_e2e}] pageable numpy) -> new numpy Y; pguresvt_params.n_gpus = {world}"
+            if world == 1:
+                from pguresvt import SVT
+
+                kws = {k: v for k, v in kw.items() if k not in ("lambda1",)}
+                s = SVT(lambda1=kw["lambda1"] if not pgure else None, **kws)
+                t0 = time.perf_counter()
+                s.denoise(Xe)
+                e2e_extra["svt_denoise_frames_per_s"] = nfr_e2e / (time.perf_counter() - t0)
+            del Ye
+        if world > 1:
+            dist.barrier(group=host_group)
+            t = torch.tensor([dt_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_e2e = float(t.item())
+        frames_e2e = nfr_e2e * args.steps
+    else:
+        # handle API with pinned host buffers: H2D of block + halo, process with the frames streamed out as they complete
+        hout = torch.empty(fsz * fps_step, dtype=torch.float64, pin_memory=True)
+        hest = np.zeros((n_total, 4), dtype=np.float64, order="F")
+        fake_base = hin.data_ptr() - fsz * r0 * 2
+        yfake = hout.data_ptr() - fsz * fb * 8
+        dp = C.POINTER(C.c_double)
+        bridge.check(L.pguresvt_stream_output(h.h, C.cast(C.c_void_p(yfake), dp)), "stream_output")
+
+        def step_e2e():
+            bridge.check(L.pguresvt_upload(h.h, C.c_void_p(fake_base)), "upload")
+            h.process()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, yblock)
+            bridge.check(L.pguresvt_download(h.h, C.cast(C.c_void_p(yfake), dp), hest.ctypes.data_as(dp)), "download")
+
         step_e2e()
-    dt_e2e = timed(step_e2e, args.steps)
+        dt_e2e = timed(step_e2e, args.steps)
+        frames_e2e = fps_step * world * args.steps
+        h2d, d2h = nbytes_in, ybytes + 32 * fps_step
+        e2e_extra["api"] = "handle API: pguresvt_upload (pinned host block + halo) -> pguresvt_process with pguresvt_stream_output -> estimates"
     sampler.stop_flag = True
 
     frames = fps_step * world * args.steps
     value = frames / dt
-    e2e = frames / dt_e2e
+    e2e = frames_e2e / dt_e2e if dt_e2e > 0 else None
     if os.environ.get("PGS_BENCH_DEBUG"):
         print(f"[rank {rank}] ms_per_step {dt / args.steps * 1e3:.1f} stages " +
               json.dumps({k: round(v / max(nst['n'], 1), 1) for k, v in acc.items() if k.startswith('ms_') or k == 'evals'}),
@@ -288,69 +395,76 @@ def main():
             dist.destroy_process_group()
         return
 
-    hbm, hbm_src, fp64, fp64_src = load_peaks()
+    hbm, hbm_src = load_peaks()
+    fp64 = dfma["sustained"] or 36.04
+    fp64_src = ("measured in this run (pguresvt_bench_dfma: DFMA, 8 chains/thread, sustained ~1 s; burst "
+                f"{dfma['burst']:.2f})" if dfma["sustained"] else "profiles/fp64_peak.json (round 1)")
     n = max(nst["n"], 1)
     stage_ms = {k: acc.get(k, 0.0) / n for k in ("ms_median", "ms_arps", "ms_svd", "ms_search_prep", "ms_search", "ms_final",
                                                    "ms_noise", "ms_total")}
     svds = acc.get("svds", 0.0) / n
     evals = acc.get("evals", 0.0) / n
     launches = acc.get("launches", 0.0) / n
-    nobj = 1 if args.fixed_lambda else 3
+    nobj = (3 if args.eps1_mode == 0 else 4) if pgure else 1
     # dominant kernel: per-patch Jacobi SVD (FP64 vector pipe).  Algorithmic flops of a thin SVD with U, S, V of an
-    # m x n matrix: 14 m n^2 + 8 n^3 = 77,400 for 16x15; one launch = one SVT object of one frame.
-    svd_launches = fps_step * nobj
-    flops_per_launch = 77400.0 * (svds / svd_launches) if svd_launches else 0.0
+    # m x n matrix: 14 m n^2 + 8 n^3: 77,400 for 16x15, 1,099,384 for 64x31; one launch = one SVT object of one
+    # frame (config 5: the three objects of a frame in one launch).
+    m_, n_ = cfg["patch"] ** 2, 2 * fw + 1
+    flop_svd = 14.0 * m_ * n_ * n_ + 8.0 * n_ ** 3
+    svd_launches = fps_step * (nobj if args.config != 5 else 1)
+    flops_per_launch = flop_svd * (svds / svd_launches) if svd_launches else 0.0
     svd_ms_per_launch = stage_ms["ms_svd"] / svd_launches if svd_launches else 0.0
     achieved_tf = flops_per_launch / (svd_ms_per_launch * 1e-3) / 1e12 if svd_ms_per_launch > 0 else 0.0
     traffic, traffic2 = None, None
     try:  # per-launch DRAM bytes of the same kernels from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
-        if size == 1024:
-            traffic = tj["k_svd16_l4"]["per_launch_avg_bytes"] if nobj == 3 else tj["k_svd16_l4"]["cold_bytes"]
-            traffic2 = tj["k_eval3"]["bytes"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if size == 1024 and args.config != 5:
+            traffic = tj["svd"]["per_launch_avg_bytes"] if nobj >= 3 else tj["svd"]["cold_bytes"]
+            traffic2 = tj["eval"]["bytes"]
     except Exception:
         pass
-    roofline = {"kernel": "k_svd16_l4 (4-lane register Jacobi, 16x15, tracked pair norms)", "bound": "fp64", "achieved": achieved_tf,
+    kname = ("k_svd16_l4 (4-lane register Jacobi, 16x15, tracked pair norms, fast rotations)" if args.config != 5 else
+             "k_svd_warp<2,2> (warp-per-matrix register Jacobi, 64x31, three objects per launch)")
+    roofline = {"kernel": kname, "bound": "fp64", "achieved": achieved_tf,
                 "peak": fp64, "unit": "TFLOP/s", "frac": achieved_tf / fp64 if fp64 else None, "traffic": traffic,
                 "peak_source": fp64_src, "note": "FP64 vector-pipe bound (tensor cores not applicable); algorithmic "
-                "flops 14mn^2+8n^3 = 77,400 per SVD x SVDs per launch / CUDA-event time of the SVD stage per launch (events on the "
-                "handle's own stream); ncu (profiles/r01) shows the FP64 pipe 53-59% busy: one-sided Jacobi executes ~2.3x the "
-                "algorithmic flops; traffic = DRAM bytes per launch from the committed ncu capture (the kernel is not HBM-bound: "
-                "~6 GB per 8 ms launch)",
+                f"flops 14mn^2+8n^3 = {flop_svd:,.0f} per SVD x SVDs per launch / CUDA-event time of the SVD stage per launch (events on "
+                "the handle's own stream); one-sided Jacobi executes ~2.3x the algorithmic flops; traffic = DRAM bytes per launch "
+                "from the committed ncu capture (profiles/traffic.json)",
                 "share_of_step": stage_ms["ms_svd"] / stage_ms["ms_total"] if stage_ms["ms_total"] else None}
-    # secondary: one lambda-search evaluation (k_eval3 + k_risk_uhat).  Algorithmic bytes per evaluation: S and q of the
-    # three objects (768 B per patch) + the surviving singular triplets of object 0 (256 B each) + the 240-entry block
-    # overlap-added per patch (1,920 B of FP64 REDs) + one pass over the Uhat accumulator, weights and u (20 B / voxel).
-    ev_per_frame = evals / fps_step if fps_step else 0
-    search_ms_per_eval = stage_ms["ms_search"] / evals if evals else 0.0
-    npatch = (size - 3) ** 2
-    trip = acc.get("eval_triplets", 0.0) / n
-    alg_bytes = (evals * (npatch * (768 + 1920) + size * size * 15 * 20) + trip * 256) / evals if evals else 0.0
-    ach_gbs = alg_bytes / (search_ms_per_eval * 1e-3) / 1e9 if search_ms_per_eval > 0 else 0.0
-    roofline2 = {"kernel": "k_eval3 + k_risk_uhat (one PGURE evaluation)", "bound": "hbm", "achieved": ach_gbs, "peak": hbm,
-                 "unit": "GB/s", "frac": ach_gbs / hbm if hbm else None, "traffic": traffic2, "peak_source": hbm_src,
-                 "note": "algorithmic bytes = S+q of 3 objects + surviving triplets of object 0 + RED block + voxel pass; "
-                 "ncu (profiles/r01): k_eval3 0.56 ms with L2 (LTS) at 78% — 111 M FP64 RED sectors per evaluation at ~200 G sectors/s, "
-                 "the L2 atomic ceiling the overlap-add pattern reaches on its own (microbench: 450 G RED/s); DRAM 1.4 GB per evaluation",
-                 "probes_per_frame": (evals + acc.get("evals_memoized", 0.0) / n) / fps_step if fps_step else None,
-                 "evals_per_frame": ev_per_frame, "algorithmic_bytes_per_eval": alg_bytes,
-                 "triplets_per_patch_per_eval": trip / (evals * npatch) if evals else None}
-    line = {"metric": "denoised frames/s (1024^2, PGURE lambda)" if not args.fixed_lambda else "denoised frames/s (fixed lambda)",
-            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": ybytes + 32 * fps_step,
-                    "ms_per_step": dt_e2e / args.steps * 1e3},
+    line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": dt_e2e / args.steps * 1e3, **e2e_extra},
             "gpu_launches": int(round(launches * args.steps)),
             "patch_svds_per_s": svds * world * args.steps / dt,
             "patch_svds_per_s_kernel": (svds / (stage_ms["ms_svd"] * 1e-3)) if stage_ms["ms_svd"] else None,
+            "svt_objects_per_patch": nobj,
             "timing": "wall clock between device synchronisations over K steps (the host-driven lambda search is part of the step), "
-                      "max over ranks; per-stage times are CUDA events on the handle's stream",
-            "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_secondary": roofline2,
-            "clocks": sampler.summary()}
+                      "max over ranks; per-stage times are CUDA events on the handle's stream, resolved after the step",
+            "stage_ms_per_step": stage_ms, "roofline": roofline,
+            "fp64_peak_tflops": dfma, "clocks": sampler.summary()}
+    if pgure and evals:
+        # secondary: one lambda-search evaluation.  achieved = DRAM bytes of one evaluation (ncu, profiles/traffic.json) / its time
+        search_ms_per_eval = stage_ms["ms_search"] / evals
+        npatch = (size - cfg["patch"] + 1) ** 2
+        trip = acc.get("eval_triplets", 0.0) / n
+        ach = (traffic2 / (search_ms_per_eval * 1e-3) / 1e9) if traffic2 else None
+        line["roofline_secondary"] = {
+            "kernel": "one PGURE evaluation (threshold + reconstruct + overlap-add + risk sums)", "bound": "hbm", "achieved": ach,
+            "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach and hbm else None, "traffic": traffic2, "peak_source": hbm_src,
+            "ms_per_eval": search_ms_per_eval,
+            "probes_per_frame": (evals + acc.get("evals_memoized", 0.0) / n) / fps_step if fps_step else None,
+            "evals_per_frame": evals / fps_step, "triplets_per_patch_per_eval": trip / (evals * npatch) if evals else None,
+            "note": "achieved = DRAM bytes per evaluation from the committed ncu capture / CUDA-event time per evaluation"}
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"], _ = cpu_reference(args, size, dict(kw))
+            line["cpu_baseline"], _, sample = cpu_reference(cfg, size, dict(kw), cfg["crop"])
+            try:
+                line["parity"] = parity_leg(cfg, dict(kw), sample, local_rank)
+            except Exception as e:  # noqa: BLE001
+                line["parity"] = {"error": str(e)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
     emit(line)

@@ -49,6 +49,10 @@ typedef struct pguresvt_params
                                   (DESIGN.md "truncated factor cache"); probes at which more triplets survive are answered
                                   exactly by re-decomposing those patches.  0: automatic (as many as half of the free HBM holds, up to all);
                                   < 0: keep the full U, S, V of every patch (svt.hpp:111-116) */
+    int32_t n_gpus;            /* one-shot entry points only: how many CUDA devices the call fans out over — the role of nJobs /
+                                  pguresvt::parallel inside PGURESVT() (pguresvt.hpp:169, utils.hpp:108-168): device, device+1, …
+                                  each take one contiguous block of frames (plus halo) on their own host thread.
+                                  0: automatic (every visible device from `device` on, at least 8 frames each); 1: `device` only */
 } pguresvt_params;
 
 enum
@@ -111,6 +115,17 @@ int pguresvt_upload(pguresvt_handle *h, const void *X_full);
 /* Same, but the source is already a device pointer to frame `first` of the resident range
  * (n_rows*n_cols*(last-first) elements of the handle's dtype). */
 int pguresvt_upload_device(pguresvt_handle *h, const void *dX_resident);
+
+/* Re-target an existing handle at another block [frame_begin, frame_end) of the same sequence without re-allocating
+ * (the block and its halo must not be longer than the ones the handle was created for).  The streaming loop of the
+ * one-shot entry points uses this; upload must follow. */
+int pguresvt_retarget(pguresvt_handle *h, uint32_t frame_begin, uint32_t frame_end);
+
+/* Stream the denoised frames to the host while the block is processed: with Y_full set (whole-sequence array as in
+ * pguresvt_download, pinned or pageable), pguresvt_process copies every frame out as soon as it is final — device→host on
+ * a copy stream into a pinned ring, then (pageable targets) host→host on a helper thread — overlapped with the SVDs of the
+ * following frames; all copies have landed when pguresvt_process returns.  NULL switches streaming off. */
+int pguresvt_stream_output(pguresvt_handle *h, double *Y_full);
 
 /* Run median prefilter + per-frame pipeline for frames [frame_begin, frame_end); results stay on device. */
 int pguresvt_process(pguresvt_handle *h);
@@ -178,6 +193,16 @@ int pguresvt_hotpixel_u16(uint16_t *seq, uint32_t n_rows, uint32_t n_cols, uint3
 int pguresvt_host_sbplx(double (*f)(double, void *), void *data, double x0, double lb, double ub, double step,
                         double ftol_rel, double xtol_abs, int maxeval, double *xbest, double *fbest, int *nevals);
 int64_t pguresvt_host_patch_ids(uint32_t N, uint32_t bs, uint32_t bo, int32_t *out, int64_t cap);
+
+/* Number of devices a one-shot call with these parameters would use for an n_frames sequence (host logic of the fan-out;
+ * n_visible < 0: ask the CUDA runtime).  pguresvt_host_frame_block: the contiguous block [*begin, *end) of rank `part` of
+ * `parts` — the partition of pguresvt::parallel (utils.hpp:150-166). */
+int pguresvt_host_plan_gpus(const pguresvt_params *p, uint32_t n_frames, int n_visible);
+int pguresvt_host_frame_block(uint32_t n_frames, int parts, int part, uint32_t *begin, uint32_t *end);
+
+/* Measured FP64 DFMA throughput of the device's vector pipe in TFLOP/s (burst = best single launch, sustained = ~1 s back
+ * to back): the roofline denominator of the SVD kernels, taken in the same job as the bench (bench.py). */
+int pguresvt_bench_dfma(int device, double *tflops_burst, double *tflops_sustained);
 
 /* Library / device info: fills name (up to len bytes), returns SM count or -1. */
 int pguresvt_device_info(int device, char *name, int len);

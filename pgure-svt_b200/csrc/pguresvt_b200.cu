@@ -9,11 +9,17 @@
 #include "../../include/pguresvt_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <random>
 #include <string>
 #include <thread>
@@ -62,6 +68,7 @@ struct pguresvt_handle
     uint32_t N = 0, nframes = 0, fb = 0, fe = 0; // square frames N x N; block [fb, fe)
     uint32_t Nt = 0, fw = 0, win = 0;            // pguresvt.hpp:57-58; window has 2*fw+1 slices
     uint32_t r0 = 0, r1 = 0;                     // resident frames [r0, r1)
+    uint32_t cap_res = 0, cap_blk = 0;           // capacity the device buffers were allocated for (pguresvt_retarget)
     size_t fsz = 0, esz = 0;
     int m = 0, n = 0, ldv = 0, M1 = 0, vecSize = 0, P = 0;
     size_t rec = 0;
@@ -138,6 +145,38 @@ struct pguresvt_handle
     int cur_ref = 0, cur_sl = 0, cur_a = 0;
     double stats[PGS_NSTATS] = {0};
     long long launches = 0;
+
+    // stage timers: event pairs recorded on the stream and resolved once at the end of pguresvt_process (no mid-stream syncs)
+    struct TimerRec
+    {
+        int slot;
+        cudaEvent_t a, b;
+    };
+    std::vector<cudaEvent_t> evpool;
+    size_t evused = 0;
+    std::vector<TimerRec> trecs;
+
+    // output streaming (pguresvt_stream_output): frames leave on copy_st as soon as they are final
+    double *sinkY = nullptr;
+    bool sink_pinned = false;
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t evFrame = nullptr;
+    static constexpr int RING = 4;
+    double *ring[RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ring_done[RING] = {nullptr, nullptr, nullptr, nullptr};
+    bool ring_busy[RING] = {false, false, false, false};
+    struct CopyJob
+    {
+        int slot;
+        uint32_t t;
+    };
+    std::deque<CopyJob> jobs;
+    int jobs_inflight = 0;
+    bool copier_stop = false;
+    std::mutex mx;
+    std::condition_variable cv;
+    std::thread copier;
+    uint64_t frames_streamed = 0;
 };
 
 #define RISK_BLOCKS 1184
@@ -178,6 +217,38 @@ static void free_all(pguresvt_handle *h)
         if (p)
             cudaFree(p);
     };
+    // helper threads first: they use the streams and buffers released below
+    if (h->noise_thread.joinable())
+        h->noise_thread.join();
+    if (h->copier.joinable())
+    {
+        {
+            std::lock_guard<std::mutex> lk(h->mx);
+            h->copier_stop = true;
+        }
+        h->cv.notify_all();
+        h->copier.join();
+    }
+    if (h->st)
+        cudaStreamSynchronize(h->st);
+    if (h->noise_st)
+        cudaStreamSynchronize(h->noise_st);
+    if (h->copy_st)
+    {
+        cudaStreamSynchronize(h->copy_st);
+        cudaStreamDestroy(h->copy_st);
+    }
+    for (int i = 0; i < pguresvt_handle::RING; i++)
+    {
+        if (h->ring[i])
+            cudaFreeHost(h->ring[i]);
+        if (h->ring_done[i])
+            cudaEventDestroy(h->ring_done[i]);
+    }
+    if (h->evFrame)
+        cudaEventDestroy(h->evFrame);
+    for (cudaEvent_t e : h->evpool)
+        cudaEventDestroy(e);
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dUp), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
     for (int i = 0; i < 4; i++)
         F(h->dAcc[i]), F(h->dFac[i]);
@@ -188,8 +259,6 @@ static void free_all(pguresvt_handle *h)
         cudaFreeHost(h->hOvf);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
         F(h->dNcost);
-    if (h->noise_thread.joinable())
-        h->noise_thread.join();
     h->noise_ws.release();
     if (h->noise_st)
         cudaStreamDestroy(h->noise_st);
@@ -261,6 +330,9 @@ static int create_impl(pguresvt_handle *h)
     h->esz = dtype_size(h->dtype);
     h->r0 = window_start(h, h->fb);
     h->r1 = window_start(h, h->fe - 1) + h->win;
+    h->cap_blk = h->fe - h->fb;
+    // any block of cap_blk frames fits: its halo is at most win - 1 frames
+    h->cap_res = std::min<uint32_t>(h->nframes, h->cap_blk + h->win - 1);
     h->nobj = 0;
     h->objs[h->nobj++] = 0;
     if (p.optimize_pgure)
@@ -288,10 +360,28 @@ static int create_impl(pguresvt_handle *h)
     }
 
     const size_t wtot = h->fsz * h->win;
-    const uint32_t nres = h->r1 - h->r0, nblk = h->fe - h->fb;
+    const uint32_t nres = h->cap_res, nblk = h->cap_blk;
+    if (h->use_l4 && p.optimize_pgure && p.rank_cache >= 0)
+    { // the full factor cache of the register-SVD path is 3,968 B per patch and object: 12 GB at 1024^2, 200 GB at 4096^2.
+      // Where it cannot fit, 16x15 goes through the truncated cache (S, q-forms, leading triplets; exact overflow path) with
+      // the generic shared-memory SVD — slower, but it runs (default-parameter sequences at 4096^2).
+        size_t freeb = 0, totb = 0;
+        CU(cudaMemGetInfo(&freeb, &totb));
+        const size_t need = h->rec * (size_t)h->P * sizeof(double) * h->nobj + wtot * 60 + h->fsz * ((size_t)nres * (h->esz + 2) + (size_t)nblk * 8);
+        if (need > freeb - freeb / 10)
+        {
+            h->use_l4 = h->use_reg_svd = h->use_fused_eval = false;
+            h->use_compact = p.eps1_mode == 0;
+            if (!h->use_compact)
+                return fail(PGS_ERR_UNSUPPORTED, "the SVD factors of %d patches x %d objects (%.1f GB) do not fit on device %d (%.1f GB free)", h->P,
+                            h->nobj, need / 1e9, p.device, freeb / 1e9);
+        }
+    }
     CU(cudaStreamCreate(&h->st));
     CU(cudaEventCreate(&h->ev[0]));
     CU(cudaEventCreate(&h->ev[1]));
+    CU(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->evFrame, cudaEventDisableTiming));
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -396,23 +486,25 @@ static int create_impl(pguresvt_handle *h)
     return PGS_OK;
 }
 
-extern "C" pguresvt_handle *pguresvt_create(int dtype, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames,
-                                            const pguresvt_params *p, uint32_t frame_begin, uint32_t frame_end)
+static pguresvt_handle *create_handle(int dtype, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, const pguresvt_params *p,
+                                      uint32_t frame_begin, uint32_t frame_end, int *rc_out)
 {
     g_err.clear();
+    int dummy;
+    int &rc = rc_out ? *rc_out : dummy;
     if (!p)
     {
-        fail(PGS_ERR_ARG, "params is NULL");
+        rc = fail(PGS_ERR_ARG, "params is NULL");
         return nullptr;
     }
     if (dtype < PGS_U8 || dtype > PGS_F64)
     {
-        fail(PGS_ERR_ARG, "unknown dtype %d", dtype);
+        rc = fail(PGS_ERR_ARG, "unknown dtype %d", dtype);
         return nullptr;
     }
     if (n_rows != n_cols)
     { // the reference assumes square frames throughout; the CLI rejects others
-        fail(PGS_ERR_ARG, "frame dimensions are not square, got %ux%u", n_cols, n_rows);
+        rc = fail(PGS_ERR_ARG, "frame dimensions are not square, got %ux%u", n_cols, n_rows);
         return nullptr;
     }
     pguresvt_handle *h = new pguresvt_handle();
@@ -422,13 +514,21 @@ extern "C" pguresvt_handle *pguresvt_create(int dtype, uint32_t n_rows, uint32_t
     h->nframes = n_frames;
     h->fb = frame_begin;
     h->fe = frame_end;
-    if (create_impl(h) != PGS_OK)
+    if ((rc = create_impl(h)) != PGS_OK)
     {
+        const std::string keep = g_err;
         free_all(h);
         delete h;
+        g_err = keep;
         return nullptr;
     }
     return h;
+}
+
+extern "C" pguresvt_handle *pguresvt_create(int dtype, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames,
+                                            const pguresvt_params *p, uint32_t frame_begin, uint32_t frame_end)
+{
+    return create_handle(dtype, n_rows, n_cols, n_frames, p, frame_begin, frame_end, nullptr);
 }
 
 extern "C" int pguresvt_resident_range(const pguresvt_handle *h, uint32_t *first, uint32_t *last)
@@ -441,6 +541,135 @@ extern "C" int pguresvt_resident_range(const pguresvt_handle *h, uint32_t *first
 }
 
 static void drop_prelaunched_noise(pguresvt_handle *h);
+static int invalidate(pguresvt_handle *h);
+
+extern "C" int pguresvt_retarget(pguresvt_handle *h, uint32_t frame_begin, uint32_t frame_end)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    if (frame_begin >= frame_end || frame_end > h->nframes)
+        return fail(PGS_ERR_ARG, "invalid frame block [%u, %u) of %u", frame_begin, frame_end, h->nframes);
+    const uint32_t r0 = window_start(h, frame_begin), r1 = window_start(h, frame_end - 1) + h->win;
+    if (frame_end - frame_begin > h->cap_blk || r1 - r0 > h->cap_res)
+        return fail(PGS_ERR_ARG, "block [%u, %u) (%u resident frames) exceeds the handle's capacity of %u frames (%u resident)", frame_begin,
+                    frame_end, r1 - r0, h->cap_blk, h->cap_res);
+    CU(cudaSetDevice(h->p.device));
+    CU(cudaStreamSynchronize(h->st));
+    h->fb = frame_begin, h->fe = frame_end, h->r0 = r0, h->r1 = r1;
+    h->xmax.assign(r1 - r0, 0.0);
+    h->xmin.assign(r1 - r0, 0.0);
+    h->zmax.assign(r1 - r0, 0.0);
+    h->est.assign((size_t)4 * (frame_end - frame_begin), 0.0);
+    invalidate(h);
+    h->uploaded = false;
+    return PGS_OK;
+}
+
+// helper thread of the output streaming: waits for a ring slot's device->host copy and moves it into the caller's array
+static void copier_main(pguresvt_handle *h)
+{
+    cudaSetDevice(h->p.device);
+    for (;;)
+    {
+        pguresvt_handle::CopyJob j;
+        {
+            std::unique_lock<std::mutex> lk(h->mx);
+            h->cv.wait(lk, [h] { return h->copier_stop || !h->jobs.empty(); });
+            if (h->jobs.empty())
+                return;
+            j = h->jobs.front();
+            h->jobs.pop_front();
+        }
+        cudaEventSynchronize(h->ring_done[j.slot]);
+        memcpy(h->sinkY + h->fsz * j.t, h->ring[j.slot], h->fsz * sizeof(double));
+        {
+            std::lock_guard<std::mutex> lk(h->mx);
+            h->ring_busy[j.slot] = false;
+            h->jobs_inflight--;
+        }
+        h->cv.notify_all();
+    }
+}
+
+extern "C" int pguresvt_stream_output(pguresvt_handle *h, double *Y_full)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->p.device));
+    h->sinkY = Y_full;
+    h->sink_pinned = false;
+    if (!Y_full)
+        return PGS_OK;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, Y_full) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        h->sink_pinned = true; // page-locked target: frames are copied straight into it
+    else
+        cudaGetLastError();
+    if (!h->sink_pinned && !h->ring[0])
+    {
+        for (int i = 0; i < pguresvt_handle::RING; i++)
+        {
+            CU(cudaMallocHost(&h->ring[i], h->fsz * sizeof(double)));
+            CU(cudaEventCreateWithFlags(&h->ring_done[i], cudaEventDisableTiming));
+        }
+        h->copier = std::thread(copier_main, h);
+    }
+    return PGS_OK;
+}
+
+// frame t (local index lt) is final in dY on the main stream: send it home on the copy stream
+static int stream_out_frame(pguresvt_handle *h, uint32_t t)
+{
+    const uint32_t lt = t - h->fb;
+    const size_t bytes = h->fsz * sizeof(double);
+    CU(cudaEventRecord(h->evFrame, h->st));
+    CU(cudaStreamWaitEvent(h->copy_st, h->evFrame, 0));
+    if (h->sink_pinned)
+    {
+        CU(cudaMemcpyAsync(h->sinkY + h->fsz * t, h->dY + h->fsz * lt, bytes, cudaMemcpyDeviceToHost, h->copy_st));
+        h->frames_streamed++;
+        return PGS_OK;
+    }
+    const int slot = (int)(h->frames_streamed % pguresvt_handle::RING);
+    {
+        std::unique_lock<std::mutex> lk(h->mx);
+        h->cv.wait(lk, [h, slot] { return !h->ring_busy[slot]; });
+        h->ring_busy[slot] = true;
+        h->jobs_inflight++;
+    }
+    cudaError_t ce = cudaMemcpyAsync(h->ring[slot], h->dY + h->fsz * lt, bytes, cudaMemcpyDeviceToHost, h->copy_st);
+    if (ce == cudaSuccess)
+        ce = cudaEventRecord(h->ring_done[slot], h->copy_st);
+    {
+        std::lock_guard<std::mutex> lk(h->mx);
+        if (ce == cudaSuccess)
+            h->jobs.push_back({slot, t});
+        else
+        {
+            h->ring_busy[slot] = false;
+            h->jobs_inflight--;
+        }
+    }
+    if (ce != cudaSuccess)
+        return fail(PGS_ERR_CUDA, "CUDA error %s while streaming frame %u to the host", cudaGetErrorString(ce), t);
+    h->cv.notify_all();
+    h->frames_streamed++;
+    return PGS_OK;
+}
+
+static int stream_out_drain(pguresvt_handle *h)
+{
+    if (!h->sinkY)
+        return PGS_OK;
+    if (!h->sink_pinned)
+    {
+        std::unique_lock<std::mutex> lk(h->mx);
+        h->cv.wait(lk, [h] { return h->jobs_inflight == 0; });
+    }
+    CU(cudaStreamSynchronize(h->copy_st));
+    return PGS_OK;
+}
+
 static int invalidate(pguresvt_handle *h)
 {
     drop_prelaunched_noise(h);
@@ -1239,18 +1468,47 @@ static int sum_u(pguresvt_handle *h, double *out)
     return PGS_OK;
 }
 
+static cudaEvent_t timer_event(pguresvt_handle *h)
+{
+    if (h->evused == h->evpool.size())
+    {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        h->evpool.push_back(e);
+    }
+    return h->evpool[h->evused++];
+}
+// adds the elapsed time of every recorded stage to its stats slot; the stream must have been synchronised
+static void resolve_timers(pguresvt_handle *h, bool keep)
+{
+    if (keep)
+        for (const auto &r : h->trecs)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess)
+                h->stats[r.slot] += ms;
+        }
+    h->trecs.clear();
+    h->evused = 0;
+}
+// Stage time by a pair of events recorded on the handle's stream; nothing waits on them until resolve_timers (the first
+// version synchronised on every stage: ~6 round trips per frame that production runs paid for nothing).
 struct StageTimer
 {
     pguresvt_handle *h;
     int slot;
-    StageTimer(pguresvt_handle *h_, int slot_) : h(h_), slot(slot_) { cudaEventRecord(h->ev[0], h->st); }
+    cudaEvent_t a;
+    StageTimer(pguresvt_handle *h_, int slot_) : h(h_), slot(slot_), a(timer_event(h_)) { cudaEventRecord(a, h->st); }
     ~StageTimer()
     {
-        cudaEventRecord(h->ev[1], h->st);
-        cudaEventSynchronize(h->ev[1]);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-        h->stats[slot] += ms;
+        cudaEvent_t b = timer_event(h);
+        cudaEventRecord(b, h->st);
+        h->trecs.push_back({slot, a, b});
+        if (h->trecs.size() > 8192)
+        { // probes never resolve: keep the pool bounded
+            cudaStreamSynchronize(h->st);
+            resolve_timers(h, false);
+        }
     }
 };
 
@@ -1453,6 +1711,8 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
         h->est[lt + (size_t)nblk * 1] = alpha;
         h->est[lt + (size_t)nblk * 2] = mu;
         h->est[lt + (size_t)nblk * 3] = sigma;
+        if (h->sinkY && (rc = stream_out_frame(h, t)))
+            return rc;
     }
     CU(cudaGetLastError());
     return PGS_OK;
@@ -1467,32 +1727,38 @@ extern "C" int pguresvt_process(pguresvt_handle *h)
     if (!h->uploaded)
         return fail(PGS_ERR_ARG, "pguresvt_process: no input uploaded");
     drop_prelaunched_noise(h);
+    CU(cudaStreamSynchronize(h->st));
+    resolve_timers(h, false); // whatever earlier probes recorded
     for (int i = 0; i < PGS_NSTATS; i++)
         h->stats[i] = 0;
     h->launches = 0;
     h->prefiltered = false;
     h->cur_t = -1;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, h->st));
-    int rc;
+    int rc = PGS_OK;
     {
-        StageTimer tm(h, 3);
-        if ((rc = prefilter(h)))
-            return rc;
+        StageTimer total(h, 9);
+        {
+            StageTimer tm(h, 3);
+            rc = prefilter(h);
+        }
+        for (uint32_t t = h->fb; t < h->fe && !rc; t++)
+            rc = process_frame(h, t);
+        if (!rc && cudaMemcpyAsync(h->dEst, h->est.data(), h->est.size() * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess)
+            rc = fail(PGS_ERR_CUDA, "CUDA error copying the estimates to the device");
     }
-    for (uint32_t t = h->fb; t < h->fe; t++)
-        if ((rc = process_frame(h, t)))
-            return rc;
-    CU(cudaMemcpyAsync(h->dEst, h->est.data(), h->est.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
-    CU(cudaEventRecord(e1, h->st));
-    CU(cudaEventSynchronize(e1));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    h->stats[9] = ms;
+    const std::string keep = g_err;
+    const cudaError_t se = cudaStreamSynchronize(h->st);
+    const int drc = stream_out_drain(h); // every streamed frame has landed in the caller's array
+    resolve_timers(h, rc == PGS_OK);
+    if (rc)
+    {
+        g_err = keep;
+        return rc;
+    }
+    if (se != cudaSuccess)
+        return fail(PGS_ERR_CUDA, "CUDA error %s at the end of pguresvt_process", cudaGetErrorString(se));
+    if (drc)
+        return drc;
     h->stats[0] = (double)h->launches;
     h->stats[11] = h->use_compact ? (double)((size_t)h->P * sizeof(double) * (64 * (size_t)h->nobj + (size_t)h->Rc * (h->m + 32)))
                                   : (double)(h->rec * (size_t)h->P * sizeof(double) * h->nobj);
@@ -1509,7 +1775,7 @@ extern "C" int pguresvt_download(pguresvt_handle *h, double *Y_full, double *est
         return fail(PGS_ERR_ARG, "null handle");
     CU(cudaSetDevice(h->p.device));
     const uint32_t nblk = h->fe - h->fb;
-    if (Y_full)
+    if (Y_full && Y_full != h->sinkY) // (a streamed block is already there)
         CU(cudaMemcpyAsync(Y_full + h->fsz * h->fb, h->dY, h->fsz * nblk * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     if (estimates_full) // (n_frames, 4) column-major
@@ -1531,47 +1797,178 @@ extern "C" int pguresvt_get_stats(const pguresvt_handle *h, double *stats)
 // ------------------------------------------------------------------------------------------------------
 // one-shot entry points
 // ------------------------------------------------------------------------------------------------------
-// One-shot entry: the whole sequence through one handle when its frames, medians and outputs fit comfortably in HBM,
-// otherwise streamed in contiguous blocks of frames (each with its fw halo frames, exactly like one slice of
-// pguresvt::parallel, utils.hpp:150-166) so that very long / very large sequences never have to be resident at once
-// (the reference keeps the whole sequence and its output in host RAM, pguresvt.hpp:44-67).
-// PGURESVT_BLOCK_FRAMES forces a block length (tests).
+// One-shot entry points = PGURESVT<T1,T2>() (pguresvt.hpp:17-172) including its fan-out (pguresvt.hpp:169 -> utils.hpp:108-168):
+//  * the frames are partitioned into contiguous blocks exactly like pguresvt::parallel (tasksPerThread = ceil(n / workers)), one
+//    block per CUDA device, each driven by its own host thread with its own handle; nothing is exchanged between devices (every
+//    frame is an independent job, pguresvt.hpp:90-167) and every device writes its frames straight into the caller's Y;
+//  * a device whose block does not fit in a quarter of its free HBM (frames + medians + outputs on top of the per-window
+//    buffers) streams it in sub-blocks through ONE handle (pguresvt_retarget): while sub-block b is processed, a helper thread
+//    stages sub-block b+1 into page-locked memory, and the denoised frames leave through pguresvt_stream_output while the
+//    following frames' SVDs run (the reference keeps the whole sequence and its output in host RAM,
+//    pguresvt.hpp:44-67).  PGURESVT_BLOCK_FRAMES forces a sub-block length (tests).
+static void frame_block(uint32_t n_frames, int parts, int part, uint32_t &b, uint32_t &e)
+{
+    const uint64_t per = ((uint64_t)n_frames + parts - 1) / parts;
+    b = (uint32_t)std::min<uint64_t>(per * part, n_frames);
+    e = (uint32_t)std::min<uint64_t>((uint64_t)b + per, n_frames);
+}
+
+static int plan_gpus(const pguresvt_params *p, uint32_t n_frames, int n_visible)
+{
+    const int avail = std::max(1, n_visible - std::max(0, p->device));
+    int n = p->n_gpus;
+    if (n <= 0) // automatic: every visible device, but no device for fewer than 8 frames (context + window buffers cost more)
+        n = std::min<int>(avail, std::max<uint32_t>(1, n_frames / 8));
+    n = std::min(n, avail);
+    n = std::min<int>(n, std::max<uint32_t>(1, n_frames));
+    return std::max(1, n);
+}
+
+extern "C" int pguresvt_host_plan_gpus(const pguresvt_params *p, uint32_t n_frames, int n_visible)
+{
+    if (!p)
+        return -1;
+    if (n_visible < 0 && cudaGetDeviceCount(&n_visible) != cudaSuccess)
+        n_visible = 0;
+    return plan_gpus(p, n_frames, n_visible);
+}
+
+extern "C" int pguresvt_host_frame_block(uint32_t n_frames, int parts, int part, uint32_t *begin, uint32_t *end)
+{
+    if (parts < 1 || part < 0 || part >= parts || !begin || !end)
+        return fail(PGS_ERR_ARG, "invalid partition %d of %d", part, parts);
+    frame_block(n_frames, parts, part, *begin, *end);
+    return PGS_OK;
+}
+
+static bool is_pinned(const void *ptr)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        return true;
+    cudaGetLastError();
+    return false;
+}
+
+// frames [fb, fe) of the sequence on device p.device; called on the device's own host thread
+static int run_device(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, pguresvt_params p, uint32_t fb,
+                      uint32_t fe, double *Y, double *estimates)
+{
+    if (fb >= fe && n_frames > 0)
+        return PGS_OK; // more devices than blocks
+    const size_t fsz = (size_t)n_rows * n_cols, esz = dtype_size(dtype);
+    uint32_t block = std::max<uint32_t>(1, fe - fb);
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && p.device >= 0 && p.device < ndev && cudaSetDevice(p.device) == cudaSuccess)
+        {
+            size_t freeb = 0, totb = 0;
+            const size_t per_frame = fsz * (esz + sizeof(uint16_t) + sizeof(double));
+            if (cudaMemGetInfo(&freeb, &totb) == cudaSuccess && per_frame > 0 && (size_t)block * per_frame > freeb / 4)
+                block = (uint32_t)std::max<size_t>(1, (freeb / 4) / per_frame);
+        }
+        if (const char *e = getenv("PGURESVT_BLOCK_FRAMES"))
+            if (atoi(e) > 0)
+                block = std::min<uint32_t>(block, (uint32_t)atoi(e));
+    }
+    int rc = PGS_OK;
+    const uint32_t fe0 = (uint32_t)std::min<uint64_t>((uint64_t)fb + block, std::max(fe, fb));
+    // (an empty sequence still goes through create once for its error message)
+    pguresvt_handle *h = create_handle(dtype, n_rows, n_cols, n_frames, &p, fb, n_frames ? fe0 : 0, &rc);
+    if (!h)
+        return rc ? rc : PGS_ERR_ARG;
+    const bool x_pinned = is_pinned(X);
+    // page-locked staging of the input sub-blocks (two buffers: one in use by the device, one being filled)
+    void *stg[2] = {nullptr, nullptr};
+    const size_t stg_bytes = fsz * esz * h->cap_res;
+    std::thread stager;
+    auto stage = [&](int buf, uint32_t r0, uint32_t r1) { memcpy(stg[buf], (const char *)X + fsz * esz * r0, fsz * esz * (r1 - r0)); };
+    auto resident = [&](uint32_t b0, uint32_t b1, uint32_t &r0, uint32_t &r1) {
+        r0 = window_start(h, b0);
+        r1 = window_start(h, b1 - 1) + h->win;
+    };
+    if (!x_pinned)
+        for (int i = 0; i < 2 && !rc; i++)
+            if (cudaMallocHost(&stg[i], stg_bytes) != cudaSuccess)
+                rc = fail(PGS_ERR_CUDA, "cannot allocate %zu bytes of page-locked staging memory", stg_bytes);
+    if (!rc)
+        rc = pguresvt_stream_output(h, Y);
+    int buf = 0;
+    if (!rc && !x_pinned)
+    {
+        uint32_t r0, r1;
+        resident(fb, fe0, r0, r1);
+        stage(0, r0, r1);
+    }
+    for (uint32_t b0 = fb; b0 < fe && !rc; b0 += block, buf ^= 1)
+    {
+        const uint32_t b1 = (uint32_t)std::min<uint64_t>((uint64_t)b0 + block, fe);
+        if (b0 != fb)
+            rc = pguresvt_retarget(h, b0, b1);
+        if (stager.joinable())
+            stager.join(); // this sub-block's frames are staged
+        if (rc)
+            break;
+        const uint32_t n0 = b1, n1 = (uint32_t)std::min<uint64_t>((uint64_t)b1 + block, fe);
+        if (!x_pinned && n0 < fe)
+        { // stage the next sub-block while this one is processed (its buffer was last read by the upload before the previous one)
+            uint32_t r0, r1;
+            resident(n0, n1, r0, r1);
+            stager = std::thread(stage, buf ^ 1, r0, r1);
+        }
+        if (x_pinned)
+            rc = pguresvt_upload(h, X);
+        else // pguresvt_upload takes the address frame 0 would have
+            rc = pguresvt_upload(h, (const char *)stg[buf] - fsz * esz * h->r0);
+        if (!rc)
+            rc = pguresvt_process(h);
+        if (!rc)
+            rc = pguresvt_download(h, nullptr, estimates);
+    }
+    if (stager.joinable())
+        stager.join();
+    const std::string keep = g_err;
+    pguresvt_destroy(h);
+    for (int i = 0; i < 2; i++)
+        if (stg[i])
+            cudaFreeHost(stg[i]);
+    g_err = keep;
+    return rc;
+}
+
 static int run_any(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames, const pguresvt_params *p,
                    double *Y, double *estimates)
 {
     if (!X || !Y || !estimates || !p)
         return fail(PGS_ERR_ARG, "null argument");
-    uint32_t block = n_frames;
-    {
-        int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) == cudaSuccess && p->device >= 0 && p->device < ndev && cudaSetDevice(p->device) == cudaSuccess)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PGS_ERR_CUDA, "no CUDA device available (the PGURE-SVT hot path has no CPU fallback)");
+    const int ng = plan_gpus(p, n_frames, ndev);
+    if (ng == 1)
+        return run_device(dtype, X, n_rows, n_cols, n_frames, *p, 0, n_frames, Y, estimates);
+    std::vector<int> rcs(ng, PGS_OK);
+    std::vector<std::string> errs(ng);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ng; g++)
+        th.emplace_back([&, g]() {
+            pguresvt_params pg = *p;
+            pg.device = p->device + g;
+            uint32_t b, e;
+            frame_block(n_frames, ng, g, b, e);
+            rcs[g] = run_device(dtype, X, n_rows, n_cols, n_frames, pg, b, e, Y, estimates);
+            if (rcs[g])
+                errs[g] = g_err; // (thread-local)
+        });
+    for (auto &t : th)
+        t.join();
+    for (int g = 0; g < ng; g++)
+        if (rcs[g])
         {
-            size_t freeb = 0, totb = 0;
-            const size_t per_frame = (size_t)n_rows * n_cols * (dtype_size(dtype) + sizeof(uint16_t) + sizeof(double));
-            if (cudaMemGetInfo(&freeb, &totb) == cudaSuccess && per_frame > 0 && (size_t)n_frames * per_frame > freeb / 4)
-                block = (uint32_t)std::max<size_t>(1, (freeb / 4) / per_frame);
+            g_err = "device " + std::to_string(p->device + g) + ": " + errs[g];
+            return rcs[g];
         }
-        if (const char *e = getenv("PGURESVT_BLOCK_FRAMES"))
-            if (atoi(e) > 0)
-                block = (uint32_t)atoi(e);
-    }
-    int rc = PGS_OK;
-    for (uint32_t fb = 0; (fb < n_frames || fb == 0) && !rc; fb += block)
-    { // (an empty sequence still goes through pguresvt_create once for its error message)
-        const uint32_t fe = (uint32_t)std::min<uint64_t>((uint64_t)fb + block, n_frames);
-        pguresvt_handle *h = pguresvt_create(dtype, n_rows, n_cols, n_frames, p, fb, fe);
-        if (!h)
-            return g_err.find("CUDA") != std::string::npos ? PGS_ERR_CUDA : PGS_ERR_ARG;
-        rc = pguresvt_upload(h, X);
-        if (!rc)
-            rc = pguresvt_process(h);
-        if (!rc)
-            rc = pguresvt_download(h, Y, estimates);
-        const std::string keep = g_err;
-        pguresvt_destroy(h);
-        g_err = keep;
-    }
-    return rc;
+    return PGS_OK;
 }
 extern "C" int pguresvt_run_u8(const uint8_t *X, uint32_t r, uint32_t c, uint32_t f, const pguresvt_params *p, double *Y, double *e)
 {
@@ -1771,6 +2168,66 @@ extern "C" int64_t pguresvt_host_patch_ids(uint32_t N, uint32_t bs, uint32_t bo,
         for (int64_t i = 0; i < (int64_t)ids.size() && i < cap; i++)
             out[i] = ids[i];
     return (int64_t)ids.size();
+}
+
+// Roofline denominator measured in the same job as the bench: FP64 DFMA throughput of the vector pipe, 8
+// independent chains per thread, sm_count * 16 CTAs of 256 threads; burst = best of 5 launches, sustained = ~1 s back to back.
+__global__ void k_dfma_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++)
+    {
+        a0 = fma(a0, b, c), a1 = fma(a1, b, c), a2 = fma(a2, b, c), a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c), a5 = fma(a5, b, c), a6 = fma(a6, b, c), a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+extern "C" int pguresvt_bench_dfma(int device, double *tflops_burst, double *tflops_sustained)
+{
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 16, iters = 20000;
+    double *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)grid * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const double flop = 2.0 * 8 * iters * (double)grid * 256;
+    double best = 0, sus = 0;
+    for (int rep = 0; rep < 6; rep++)
+    {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<grid, 256>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0)
+            best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    {
+        const int n = 30;
+        cudaEventRecord(e0);
+        for (int i = 0; i < n; i++)
+            k_dfma_peak<<<grid, 256>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0)
+            sus = flop * n / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CU(cudaGetLastError());
+    if (tflops_burst)
+        *tflops_burst = best;
+    if (tflops_sustained)
+        *tflops_sustained = sus;
+    return PGS_OK;
 }
 
 #include "hotpixel.cuh"

@@ -40,6 +40,7 @@ class Params(C.Structure):
         ("eps1_mode", C.c_int32),
         ("svd_kernel", C.c_int32),
         ("rank_cache", C.c_int32),
+        ("n_gpus", C.c_int32),
     ]
 
 
@@ -80,6 +81,10 @@ def load():
     L.pguresvt_upload.argtypes = [vp, vp]
     L.pguresvt_upload_device.argtypes = [vp, vp]
     L.pguresvt_process.argtypes = [vp]
+    L.pguresvt_retarget.argtypes = [vp, u32, u32]
+    L.pguresvt_stream_output.argtypes = [vp, dp]
+    L.pguresvt_host_plan_gpus.argtypes = [pp, u32, C.c_int]
+    L.pguresvt_host_frame_block.argtypes = [u32, C.c_int, C.c_int, C.POINTER(u32), C.POINTER(u32)]
     L.pguresvt_device_output.argtypes = [vp]
     L.pguresvt_device_output.restype = vp
     L.pguresvt_device_estimates.argtypes = [vp]
@@ -94,11 +99,24 @@ def load():
     L.pguresvt_probe_perturbations.argtypes = [vp, C.POINTER(C.c_int8), C.POINTER(C.c_int8)]
     L.pguresvt_probe_noise.argtypes = [vp, u32, dp, dp, dp]
     L.pguresvt_hotpixel_u16.argtypes = [C.POINTER(C.c_uint16), u32, u32, u32, C.c_double, C.c_int]
+    L.pguresvt_bench_dfma.argtypes = [C.c_int, dp, dp]
     L.pguresvt_device_info.argtypes = [C.c_int, C.c_char_p, C.c_int]
     L.pguresvt_host_patch_ids.argtypes = [u32, u32, u32, C.POINTER(C.c_int32), C.c_int64]
     L.pguresvt_host_patch_ids.restype = C.c_int64
     _lib = L
     return L
+
+
+def plan_gpus(n_frames, n_visible=-1, **kw):
+    """Number of devices a one-shot call with these parameters fans out over (host logic, no GPU needed with n_visible >= 0)."""
+    p = make_params(**kw)
+    return load().pguresvt_host_plan_gpus(C.byref(p), int(n_frames), int(n_visible))
+
+
+def frame_block(n_frames, parts, part):
+    b, e = C.c_uint32(0), C.c_uint32(0)
+    check(load().pguresvt_host_frame_block(int(n_frames), int(parts), int(part), C.byref(b), C.byref(e)), "frame_block")
+    return b.value, e.value
 
 
 def last_error():
@@ -113,7 +131,11 @@ def check(rc, what="pguresvt"):
 def make_params(trajectory_length=15, patch_size=4, patch_overlap=1, motion_window=7, motion_filter=5, noise_method=4,
                 max_iter=500, n_jobs=-1, random_seed=-1, optimize_pgure=True, exponential_weighting=True,
                 motion_estimation=True, lambda1=0.0, noise_alpha=-1.0, noise_mu=-1.0, noise_sigma=-1.0, tol=1e-7,
-                device=None, eps1_mode=None, svd_kernel=None, rank_cache=None):
+                device=None, eps1_mode=None, svd_kernel=None, rank_cache=None, n_gpus=None):
+    if n_gpus is None:
+        # one-shot calls fan out over every visible GPU (the role of n_jobs = -1 in the reference), except inside a
+        # one-process-per-GPU launch (torchrun sets LOCAL_RANK), where every rank keeps to its own device
+        n_gpus = int(os.environ.get("PGURESVT_NGPUS", "1" if "LOCAL_RANK" in os.environ else "0"))
     if device is None:
         device = int(os.environ.get("PGURESVT_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     if eps1_mode is None:
@@ -125,7 +147,8 @@ def make_params(trajectory_length=15, patch_size=4, patch_overlap=1, motion_wind
     return Params(int(trajectory_length), int(patch_size), int(patch_overlap), int(motion_window), int(motion_filter),
                   int(noise_method), int(max_iter), int(n_jobs), int(random_seed), int(bool(optimize_pgure)),
                   int(bool(exponential_weighting)), int(bool(motion_estimation)), float(lambda1), float(noise_alpha),
-                  float(noise_mu), float(noise_sigma), float(tol), int(device), int(eps1_mode), int(svd_kernel), int(rank_cache))
+                  float(noise_mu), float(noise_sigma), float(tol), int(device), int(eps1_mode), int(svd_kernel), int(rank_cache),
+                  int(n_gpus))
 
 
 def _run(entry, dtype, input_images, **kw):
@@ -204,6 +227,16 @@ class Handle:
 
     def process(self):
         check(self.L.pguresvt_process(self.h), "process")
+
+    def retarget(self, frame_begin, frame_end):
+        check(self.L.pguresvt_retarget(self.h, frame_begin, frame_end), "retarget")
+        self.fb, self.fe = frame_begin, frame_end
+
+    def stream_output(self, Y):
+        """Y: whole-sequence (rows, cols, frames) float64 F-order array the frames are streamed into during process()."""
+        self._Ysink = Y
+        ptr = None if Y is None else Y.ctypes.data_as(C.POINTER(C.c_double))
+        check(self.L.pguresvt_stream_output(self.h, ptr), "stream_output")
 
     def device_output(self):
         return self.L.pguresvt_device_output(self.h)

@@ -129,7 +129,8 @@ int main(int argc, char **argv)
     if (hotPixelThreshold >= 0.0)
     {
         t0 = std::chrono::high_resolution_clock::now();
-        const int rc = pguresvt_hotpixel_u16(inputSeq.memptr(), H, W, (uint32_t)inputSeq.n_slices, hotPixelThreshold, 0);
+        const int rc = pguresvt_hotpixel_u16(inputSeq.memptr(), H, W, (uint32_t)inputSeq.n_slices, hotPixelThreshold,
+                                             std::getenv("PGURESVT_DEVICE") ? std::atoi(std::getenv("PGURESVT_DEVICE")) : 0);
         if (rc != 0)
         {
             pguresvt::Print(std::cerr, "**ERROR**\nOutlier filter failed: ", pguresvt_last_error(), "\n");

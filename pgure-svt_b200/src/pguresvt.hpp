@@ -8,6 +8,7 @@
 #define PGURESVT_B200_PGURESVT_HPP
 
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #ifdef PGURESVT_USE_ARMADILLO
@@ -68,6 +69,11 @@ uint32_t PGURESVT(arma::Cube<T2> &Y,
     p.mu_est = muEst;
     p.sigma_est = sigmaEst;
     p.tol = tol;
+    // extensions: the call fans out over every visible GPU by default (n_gpus = 0), like nJobs = -1 over host threads
+    if (const char *e = std::getenv("PGURESVT_DEVICE"))
+        p.device = std::atoi(e);
+    if (const char *e = std::getenv("PGURESVT_NGPUS"))
+        p.n_gpus = std::atoi(e);
 
     const uint32_t nr = (uint32_t)X.n_rows, nc = (uint32_t)X.n_cols, nf = (uint32_t)X.n_slices;
     int rc;

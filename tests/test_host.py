@@ -26,7 +26,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_params_struct_layout_matches_header():
     # 4*u32, i64, 2*u32, 2*i64, 3*i32 (+pad), 5*f64, 4*i32
-    assert C.sizeof(bridge.Params) == 16 + 8 + 8 + 16 + 16 + 40 + 16
+    assert C.sizeof(bridge.Params) == 16 + 8 + 8 + 16 + 16 + 40 + 16 + 8  # + n_gpus and tail padding
     assert bridge.Params.lambda_est.offset == 64
 
 
@@ -266,3 +266,19 @@ def test_qform_identity_behind_the_compact_cache():
         vhat = np.divide(direct_acc, weights, out=np.zeros_like(direct_acc), where=weights > 0)
         direct = float((delta2 * vhat).sum())
         assert abs(direct - via_q) <= 1e-10 * max(1.0, abs(direct))
+
+
+def test_plan_gpus_and_frame_blocks_match_reference_partition():
+    """The one-shot entry's fan-out (pguresvt_params.n_gpus) is host logic: partition of utils.hpp:150-166."""
+    from pguresvt.distributed import frame_block
+
+    assert bridge.plan_gpus(1000, n_visible=8, n_gpus=0) == 8
+    assert bridge.plan_gpus(1000, n_visible=8, n_gpus=2) == 2
+    assert bridge.plan_gpus(16, n_visible=8, n_gpus=0) == 2      # automatic: at least 8 frames per device
+    assert bridge.plan_gpus(7, n_visible=8, n_gpus=0) == 1
+    assert bridge.plan_gpus(1000, n_visible=8, n_gpus=0, device=6) == 2
+    assert bridge.plan_gpus(1000, n_visible=1, n_gpus=4) == 1
+    assert bridge.plan_gpus(3, n_visible=8, n_gpus=8) == 3
+    for n, w in [(16, 2), (17, 2), (1000, 8), (5, 8), (23, 4)]:
+        for r in range(w):
+            assert bridge.frame_block(n, w, r) == frame_block(r, w, n)
