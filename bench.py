@@ -72,18 +72,30 @@ def make_block(size, nfr, seed, alpha=0.1, mu=0.1, sigma=0.1):
 
 
 class ClockSampler(threading.Thread):
+    """One `nvidia-smi -lms` child for the whole run (started before the big allocations: a fork per sample of a process
+    that maps hundreds of GB of CUDA address space stalls every thread that needs the mm lock — page faults, cudaMalloc)."""
+
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.reasons, self.stop_flag, self.maxmhz = gpu_index, [], set(), False, None
-
-    def run(self):
+        self.gpu, self.samples, self.reasons, self.maxmhz, self.active = gpu_index, [], set(), None, False
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        period = int(float(os.environ.get("PGS_BENCH_SAMPLER_PERIOD", "0.2")) * 1000)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          f"-lms", str(period)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def run(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            if not self.active:
+                continue
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                out = line.strip().split(",")
                 self.samples.append(float(out[0]))
                 self.maxmhz = float(out[1])
                 for n, v in zip(names, out[2:]):
@@ -91,7 +103,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(float(os.environ.get("PGS_BENCH_SAMPLER_PERIOD", "0.2")))
+
+    def stop(self):
+        self.active = False
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
 
     def summary(self):
         s = sorted(self.samples)
@@ -249,6 +268,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         host_group = dist.new_group(backend="gloo")  # host-side barrier for the leg in which rank 0 drives every device
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     L = bridge.load()
     # FP64 roofline denominator, measured in this job (rank 0's device, before anything else runs on it)
     dfma = {"burst": None, "sustained": None}
@@ -311,9 +333,8 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if sampler:
+        sampler.active = True
     acc = {}
     nst = {"n": 0}
 
@@ -381,7 +402,8 @@ def main():
         frames_e2e = fps_step * world * args.steps
         h2d, d2h = nbytes_in, ybytes + 32 * fps_step
         e2e_extra["api"] = "handle API: pguresvt_upload (pinned host block + halo) -> pguresvt_process with pguresvt_stream_output -> estimates"
-    sampler.stop_flag = True
+    if sampler:
+        sampler.stop()
 
     frames = fps_step * world * args.steps
     value = frames / dt

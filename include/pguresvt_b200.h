@@ -89,6 +89,11 @@ int pguresvt_run_f32(const float *X, uint32_t n_rows, uint32_t n_cols, uint32_t 
 int pguresvt_run_f64(const double *X, uint32_t n_rows, uint32_t n_cols, uint32_t n_frames,
                      const pguresvt_params *p, double *Y, double *estimates);
 
+/* The one-shot entry points keep one handle per device between calls (device buffers of the last frame size / parameter
+ * set, page-locked staging): a later call with the same configuration re-targets it instead of re-allocating.  This frees
+ * them.  PGURESVT_NO_CACHE=1 in the environment disables the cache. */
+void pguresvt_release_cached(void);
+
 /* Message of the last error on the calling thread ("" if none).  Replaces the C++ exceptions that escape
  * the reference's worker threads (SURVEY §5 "Failure detection"). */
 const char *pguresvt_last_error(void);
@@ -179,6 +184,11 @@ int pguresvt_probe_reconstruct(pguresvt_handle *h, uint32_t t, double lambda, do
 int pguresvt_probe_perturbations(pguresvt_handle *h, int8_t *delta1, int8_t *delta2neg);
 /* Noise estimate of frame t's window (noise.hpp:35-153): in/out alpha, mu, sigma (< 0 = estimate). */
 int pguresvt_probe_noise(pguresvt_handle *h, uint32_t t, double *alpha, double *mu, double *sigma);
+
+/* arma::accu(u) of frame t's max-normalised window — the start point of the lambda search times Nx*Ny*Nt
+ * (pguresvt.hpp:139) and the second sum of the risk (pgure.hpp:136) — in Armadillo's order (two sequential
+ * accumulators), bit for bit. */
+int pguresvt_probe_window_sum(pguresvt_handle *h, uint32_t t, double *sum);
 
 /* Hot-pixel prefilter (src/hotpixel.hpp:19-64, called from src/PGURE-SVT.cpp:171-179): in place on a host
  * uint16 sequence. */

@@ -27,6 +27,7 @@
 
 #include "kernels.cuh"
 #include "compact.cuh"
+#include "tile_eval.cuh"
 #include "noise.cuh"
 #include "sbplx1d.hpp"
 
@@ -77,6 +78,18 @@ struct pguresvt_handle
     bool use_reg_svd = false; // any register-resident 16x15 kernel
     bool use_l4 = false;      // 4-lanes-per-matrix kernel (S in slot order, S[15] = sigma_max)
     bool use_fused_eval = false;
+    bool use_tile = false;       // atomics-free gather evaluation (tile_eval.cuh) on top of the fused path
+    bool frame_fallback = false; // a third triplet survived at some probe of this frame: general k_eval3 path from there on
+    int *dBinCnt = nullptr, *dBinStart = nullptr, *dScanSums = nullptr;
+    TgEntry *dEnt = nullptr;
+    double *dHead = nullptr, *dTilePart = nullptr;
+    double2 *dFth = nullptr;
+    int tile_r = 0, tile_c = 0;
+    // arma::accu(u) bit for bit (k_accu_seq) on its own stream beside the ARPS / SVD stages
+    cudaStream_t sum_st = nullptr;
+    cudaEvent_t evU = nullptr, evSum = nullptr;
+    double *dSum2 = nullptr, *hSum2 = nullptr;
+    bool sum_pending = false;
     bool use_warp_svd = false; // 64 x n Casorati matrices: warp-per-matrix register Jacobi (compact.cuh)
     bool use_warp3 = false;    // compact cache + warp kernel: the three PGURE objects of a patch in one launch, warm-started
     bool use_compact = false;  // truncated factor cache (S, q-forms, leading Rc triplets of object 0), compact.cuh
@@ -177,6 +190,9 @@ struct pguresvt_handle
     std::condition_variable cv;
     std::thread copier;
     uint64_t frames_streamed = 0;
+    // page-locked staging of the one-shot entry's input sub-blocks (kept with the handle so that a cached handle keeps them)
+    void *stg[2] = {nullptr, nullptr};
+    size_t stg_bytes = 0;
 };
 
 #define RISK_BLOCKS 1184
@@ -247,6 +263,9 @@ static void free_all(pguresvt_handle *h)
     }
     if (h->evFrame)
         cudaEventDestroy(h->evFrame);
+    for (int i = 0; i < 2; i++)
+        if (h->stg[i])
+            cudaFreeHost(h->stg[i]);
     for (cudaEvent_t e : h->evpool)
         cudaEventDestroy(e);
     F(h->dX), F(h->dZ), F(h->dTmp16), F(h->dU), F(h->dUp), F(h->dW), F(h->dPos), F(h->dArpsF), F(h->dArpsB), F(h->dIds), F(h->dCnt);
@@ -255,6 +274,19 @@ static void free_all(pguresvt_handle *h)
     for (int i = 0; i < 4; i++)
         F(h->dSc[i]), F(h->dQc[i]);
     F(h->dLead), F(h->dOvf), F(h->dFacScratch), F(h->dUn), F(h->dAccScale);
+    if (h->sum_st)
+    {
+        cudaStreamSynchronize(h->sum_st);
+        cudaStreamDestroy(h->sum_st);
+    }
+    if (h->evU)
+        cudaEventDestroy(h->evU);
+    if (h->evSum)
+        cudaEventDestroy(h->evSum);
+    if (h->hSum2)
+        cudaFreeHost(h->hSum2);
+    F(h->dSum2);
+    F(h->dBinCnt), F(h->dBinStart), F(h->dScanSums), F(h->dEnt), F(h->dHead), F(h->dTilePart), F(h->dFth);
     if (h->hOvf)
         cudaFreeHost(h->hOvf);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
@@ -387,6 +419,11 @@ static int create_impl(pguresvt_handle *h)
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&h->noise_st, cudaStreamNonBlocking, hi));
         CU(cudaEventCreateWithFlags(&h->evWin, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithPriority(&h->sum_st, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&h->evU, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->evSum, cudaEventDisableTiming));
+        CU(cudaMalloc(&h->dSum2, 2 * sizeof(double)));
+        CU(cudaMallocHost(&h->hSum2, 2 * sizeof(double)));
     }
     CU(cudaMalloc(&h->dX, h->fsz * nres * h->esz));
     if (p.median_size > 0)
@@ -441,11 +478,24 @@ static int create_impl(pguresvt_handle *h)
         if (wtot >= ((size_t)1 << 31))
             return fail(PGS_ERR_UNSUPPORTED, "window of %zu voxels exceeds the fused evaluation kernel's 32-bit indexing", wtot);
         CU(cudaMalloc(&h->dC4, wtot * sizeof(double)));
-        CU(cudaMalloc(&h->dPartialE, (size_t)4 * h->eval_blocks * sizeof(double)));
-        CU(cudaMalloc(&h->dKpart, (size_t)4 * h->eval_blocks * sizeof(int)));
+        CU(cudaMalloc(&h->dPartialE, ((size_t)4 * h->eval_blocks + 64) * sizeof(double)));
+        CU(cudaMalloc(&h->dKpart, ((size_t)4 * h->eval_blocks + 64) * sizeof(int)));
 
         for (int k = 0; k < 3; k++)
             CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
+        h->use_tile = !(getenv("PGURESVT_TILE_EVAL") && atoi(getenv("PGURESVT_TILE_EVAL")) == 0);
+        if (h->use_tile)
+        {
+            const size_t nbins = h->fsz * h->win;
+            h->tile_r = cdiv(h->N, TG_VR), h->tile_c = cdiv(h->N, TG_VC);
+            CU(cudaMalloc(&h->dBinCnt, nbins * sizeof(int)));
+            CU(cudaMalloc(&h->dBinStart, (nbins + 1) * sizeof(int)));
+            CU(cudaMalloc(&h->dScanSums, ((size_t)cdiv(nbins, SCAN_ITEMS) + 1) * sizeof(int)));
+            CU(cudaMalloc(&h->dEnt, (size_t)h->P * h->win * sizeof(TgEntry)));
+            CU(cudaMalloc(&h->dHead, (size_t)TG_HEAD * h->P * sizeof(double)));
+            CU(cudaMalloc(&h->dFth, (size_t)h->P * sizeof(double2)));
+            CU(cudaMalloc(&h->dTilePart, (size_t)2 * h->tile_r * h->tile_c * h->win * sizeof(double)));
+        }
     }
     CU(cudaMalloc(&h->dPartial, (size_t)RISK_BLOCKS * 8 * sizeof(double)));
     CU(cudaMalloc(&h->dOut, 16 * sizeof(double)));
@@ -543,16 +593,24 @@ extern "C" int pguresvt_resident_range(const pguresvt_handle *h, uint32_t *first
 static void drop_prelaunched_noise(pguresvt_handle *h);
 static int invalidate(pguresvt_handle *h);
 
-extern "C" int pguresvt_retarget(pguresvt_handle *h, uint32_t frame_begin, uint32_t frame_end)
+// n_frames may change too (a cached handle serving another sequence of the same frame size and parameters)
+static int retarget_impl(pguresvt_handle *h, uint32_t n_frames, uint32_t frame_begin, uint32_t frame_end)
 {
     if (!h)
         return fail(PGS_ERR_ARG, "null handle");
-    if (frame_begin >= frame_end || frame_end > h->nframes)
-        return fail(PGS_ERR_ARG, "invalid frame block [%u, %u) of %u", frame_begin, frame_end, h->nframes);
+    if (n_frames < h->win)
+        return fail(PGS_ERR_ARG, "sequence has %u frames, fewer than the %u-frame window", n_frames, h->win);
+    if (frame_begin >= frame_end || frame_end > n_frames)
+        return fail(PGS_ERR_ARG, "invalid frame block [%u, %u) of %u", frame_begin, frame_end, n_frames);
+    const uint32_t keep_n = h->nframes;
+    h->nframes = n_frames;
     const uint32_t r0 = window_start(h, frame_begin), r1 = window_start(h, frame_end - 1) + h->win;
     if (frame_end - frame_begin > h->cap_blk || r1 - r0 > h->cap_res)
+    {
+        h->nframes = keep_n;
         return fail(PGS_ERR_ARG, "block [%u, %u) (%u resident frames) exceeds the handle's capacity of %u frames (%u resident)", frame_begin,
                     frame_end, r1 - r0, h->cap_blk, h->cap_res);
+    }
     CU(cudaSetDevice(h->p.device));
     CU(cudaStreamSynchronize(h->st));
     h->fb = frame_begin, h->fe = frame_end, h->r0 = r0, h->r1 = r1;
@@ -563,6 +621,13 @@ extern "C" int pguresvt_retarget(pguresvt_handle *h, uint32_t frame_begin, uint3
     invalidate(h);
     h->uploaded = false;
     return PGS_OK;
+}
+
+extern "C" int pguresvt_retarget(pguresvt_handle *h, uint32_t frame_begin, uint32_t frame_end)
+{
+    if (!h)
+        return fail(PGS_ERR_ARG, "null handle");
+    return retarget_impl(h, h->nframes, frame_begin, frame_end);
 }
 
 // helper thread of the output streaming: waits for a ring slot's device->host copy and moves it into the caller's array
@@ -1422,8 +1487,81 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     return PGS_OK;
 }
 
+// Per frame, after the SVDs and the q-forms: head records and the per-slice CSR "patches by destination" (tile_eval.cuh)
+static int tile_prepare(pguresvt_handle *h)
+{
+    const size_t nbins = h->fsz * h->win;
+    const int nb = cdiv(nbins, SCAN_ITEMS);
+    const int *ids = h->P == h->vecSize ? nullptr : h->dIds;
+    const int grid = std::min(cdiv((long long)h->P * h->win, 256), h->sm_count * 32);
+    CU(cudaMemsetAsync(h->dBinCnt, 0, nbins * sizeof(int), h->st));
+    k_bin_count<<<grid, 256, 0, h->st>>>(h->dPos, ids, h->P, h->vecSize, h->N, h->win, h->dBinCnt);
+    LAUNCHED(h);
+    k_scan_sums<<<nb, SCAN_THREADS, 0, h->st>>>(h->dBinCnt, nbins, h->dScanSums);
+    LAUNCHED(h);
+    k_scan_block_sums<<<1, 1024, 0, h->st>>>(h->dScanSums, nb);
+    LAUNCHED(h);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, h->st>>>(h->dBinCnt, nbins, h->dScanSums, nb, h->dBinStart);
+    LAUNCHED(h);
+    CU(cudaMemsetAsync(h->dBinCnt, 0, nbins * sizeof(int), h->st)); // reused as the fill cursors
+    k_bin_fill<<<grid, 256, 0, h->st>>>(h->dPos, ids, h->P, h->vecSize, h->N, h->win, h->dBinStart, h->dBinCnt, h->dFac[0], h->dEnt);
+    LAUNCHED(h);
+    k_bin_sort<<<std::min(cdiv(nbins, 256), h->sm_count * 32), 256, 0, h->st>>>(h->dBinStart, nbins, h->dEnt);
+    LAUNCHED(h);
+    k_head_pack<<<cdiv((long long)h->P * 4, 256), 256, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->P,
+                                                                     h->dHead);
+    LAUNCHED(h);
+    CU(cudaGetLastError());
+    h->frame_fallback = false;
+    return PGS_OK;
+}
+
+static int objective_fused(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms);
+
+// One evaluation of PGURE::CalculatePGURE through the gather path: thresholds + second-difference sum per patch, then one
+// CTA per output tile and slice (no atomics, no accumulator cube), then the fixed-order reduction.
+static int objective_tile(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
+{
+    if (h->frame_fallback)
+        return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
+    const int nw = cdiv(h->P, 32), ntile = h->tile_r * h->tile_c * (int)h->win;
+    k_thresh<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, h->p.exp_weighting, h->dFth, h->dPartialE, h->dKpart, h->dNeedQ);
+    LAUNCHED(h);
+    k_tile_eval<0><<<dim3(h->tile_r, h->tile_c, h->win), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dFth, h->dU, h->dCnt, h->N, 0, 1.0,
+                                                                          nullptr, h->dTilePart);
+    LAUNCHED(h);
+    k_reduce_eval<<<1, 1024, 0, h->st>>>(h->dTilePart, ntile, h->dPartialE, h->dKpart, nw, h->dOut);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hOut, h->dOut, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (*reinterpret_cast<const int *>(h->hOut + 4))
+    { // a third triplet of some object survived at this lambda: all q-forms, general evaluation for the rest of the frame
+        int rc = launch_qform(h, SVD16_N);
+        if (rc)
+            return rc;
+        h->stats[18] += 1;
+        h->frame_fallback = true;
+        return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
+    }
+    h->stats[16] += h->hOut[3];
+    const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
+    const double sigmasq = sigma * sigma;
+    const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
+    const double OoN = 1.0 / ((double)h->N * h->N * h->win);
+    *value = OoN * (s1 - (alpha + mu) * s2 + (2 / eps1 * s3) - (2 * sigmasq * alpha / (eps2 * eps2) * s4) + (2 * mu * s5) + mu) -
+             sigmasq;
+    if (terms)
+    {
+        terms[0] = s1, terms[1] = s2, terms[2] = s3, terms[3] = s4, terms[4] = s5;
+    }
+    h->stats[2] += 1;
+    return PGS_OK;
+}
+
 static int objective(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
 {
+    if (h->use_tile)
+        return objective_tile(h, lambda, alpha, mu, sigma, value, terms);
     if (h->use_fused_eval)
         return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
     if (h->use_compact)
@@ -1455,16 +1593,28 @@ static int objective(pguresvt_handle *h, double lambda, double alpha, double mu,
     return PGS_OK;
 }
 
-static int sum_u(pguresvt_handle *h, double *out)
+// accu(u) of the current window in Armadillo's order (two sequential accumulators), started right after the window is
+// normalised and collected when the SVD launches are in flight
+static int sum_u_launch(pguresvt_handle *h)
 {
     const size_t wtot = h->fsz * h->win;
-    k_sum<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, wtot, h->dPartial);
+    CU(cudaEventRecord(h->evU, h->st));
+    CU(cudaStreamWaitEvent(h->sum_st, h->evU, 0));
+    k_accu_seq<<<2, AS_THREADS, 0, h->sum_st>>>(h->dU, wtot, h->dSum2);
     LAUNCHED(h);
-    k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 1, h->dOut);
-    LAUNCHED(h);
-    CU(cudaMemcpyAsync(h->hOut, h->dOut, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
-    *out = h->hOut[0];
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->hSum2, h->dSum2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->sum_st));
+    CU(cudaEventRecord(h->evSum, h->sum_st));
+    h->sum_pending = true;
+    return PGS_OK;
+}
+static int sum_u_wait(pguresvt_handle *h)
+{
+    if (!h->sum_pending)
+        return PGS_OK;
+    CU(cudaEventSynchronize(h->evSum));
+    h->cur_sumU = h->hSum2[0] + h->hSum2[1]; // acc1 + acc2
+    h->sum_pending = false;
     return PGS_OK;
 }
 
@@ -1525,6 +1675,8 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     h->cur_t = -1;
     if ((rc = stage_window(h, t)))
         return rc;
+    if (h->p.optimize_pgure && (rc = sum_u_launch(h)))
+        return rc;
     if (h->noise_req)
     { // the estimator reads only the window cube: let it run beside ARPS and the SVDs on its own high-priority stream
         CU(cudaEventRecord(h->evWin, h->st));
@@ -1554,8 +1706,6 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
             k_c4<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dCnt, h->dD2, h->d2Neg, h->d2Pos, wtot, h->dC4);
             LAUNCHED(h);
         }
-        if ((rc = sum_u(h, &h->cur_sumU)))
-            return rc;
     }
     {
         StageTimer tm(h, 5);
@@ -1591,7 +1741,11 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         StageTimer tm(h, 17);
         if ((rc = launch_qform(h, QFORM_LAZY_K)))
             return rc;
+        if (h->use_tile && (rc = tile_prepare(h)))
+            return rc;
     }
+    if ((rc = sum_u_wait(h)))
+        return rc;
     h->cur_t = t;
     return PGS_OK;
 }
@@ -1700,12 +1854,24 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
         if (!p.optimize_pgure)
             if ((rc = stage_count(h, h->cur_sl)))
                 return rc;
-        if ((rc = launch_recon(h, 0, lambda, h->cur_sl)))
-            return rc;
         const uint32_t lt = t - h->fb;
-        k_finalize<<<std::min(cdiv(h->fsz, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dAccScale, h->dCnt, h->fsz * h->cur_sl, h->fsz,
-                                                                                    h->cur_uMax, h->dY + h->fsz * lt);
-        LAUNCHED(h);
+        if (h->use_tile && p.optimize_pgure && !h->frame_fallback)
+        { // output slice straight from the gather kernel (thresholds of the final lambda; no probe of this frame needed more
+          // than two triplets, and the final lambda is one of the probes)
+            k_thresh<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, p.exp_weighting, h->dFth, h->dPartialE, h->dKpart, h->dNeedQ);
+            LAUNCHED(h);
+            k_tile_eval<1><<<dim3(h->tile_r, h->tile_c, 1), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dFth, h->dU, h->dCnt, h->N,
+                                                                             h->cur_sl, h->cur_uMax, h->dY + h->fsz * lt, nullptr);
+            LAUNCHED(h);
+        }
+        else
+        {
+            if ((rc = launch_recon(h, 0, lambda, h->cur_sl)))
+                return rc;
+            k_finalize<<<std::min(cdiv(h->fsz, 256), h->sm_count * 8), 256, 0, h->st>>>(h->dAcc[0], h->dAccScale, h->dCnt, h->fsz * h->cur_sl,
+                                                                                        h->fsz, h->cur_uMax, h->dY + h->fsz * lt);
+            LAUNCHED(h);
+        }
         const uint32_t nblk = h->fe - h->fb;
         h->est[lt + (size_t)nblk * 0] = lambda;
         h->est[lt + (size_t)nblk * 1] = alpha;
@@ -1841,6 +2007,62 @@ extern "C" int pguresvt_host_frame_block(uint32_t n_frames, int parts, int part,
     return PGS_OK;
 }
 
+// One handle per device is kept between one-shot calls (like a plan cache): creating a handle allocates and clears ~13 GB at
+// 1024^2 and page-locks the staging buffers (~110 ms create + destroy, 8 % of a 32-frame call); a later call with the same
+// frame size, dtype and parameters re-targets it instead.  pguresvt_release_cached() frees them; PGURESVT_NO_CACHE=1 disables.
+static std::mutex g_cache_mx;
+static std::vector<pguresvt_handle *> g_cache;
+
+static bool same_config(const pguresvt_handle *h, int dtype, uint32_t N, const pguresvt_params &p)
+{
+    const pguresvt_params &q = h->p;
+    return h->dtype == dtype && h->N == N && q.device == p.device && q.traj_length == p.traj_length && q.block_size == p.block_size &&
+           q.block_overlap == p.block_overlap && q.motion_window == p.motion_window && q.median_size == p.median_size &&
+           q.noise_method == p.noise_method && q.max_iter == p.max_iter && q.random_seed == p.random_seed &&
+           q.optimize_pgure == p.optimize_pgure && q.exp_weighting == p.exp_weighting && q.motion_estimation == p.motion_estimation &&
+           q.lambda_est == p.lambda_est && q.alpha_est == p.alpha_est && q.mu_est == p.mu_est && q.sigma_est == p.sigma_est &&
+           q.tol == p.tol && q.eps1_mode == p.eps1_mode && q.svd_kernel == p.svd_kernel && q.rank_cache == p.rank_cache;
+}
+static pguresvt_handle *cache_take(int dtype, uint32_t N, const pguresvt_params &p)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mx);
+    for (size_t i = 0; i < g_cache.size(); i++)
+        if (same_config(g_cache[i], dtype, N, p))
+        {
+            pguresvt_handle *h = g_cache[i];
+            g_cache.erase(g_cache.begin() + i);
+            return h;
+        }
+    return nullptr;
+}
+static void cache_put(pguresvt_handle *h)
+{
+    pguresvt_handle *old = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mx);
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i]->p.device == h->p.device)
+            { // one handle per device
+                old = g_cache[i];
+                g_cache.erase(g_cache.begin() + i);
+                break;
+            }
+        g_cache.push_back(h);
+    }
+    if (old)
+        pguresvt_destroy(old);
+}
+extern "C" void pguresvt_release_cached(void)
+{
+    std::vector<pguresvt_handle *> all;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mx);
+        all.swap(g_cache);
+    }
+    for (pguresvt_handle *h : all)
+        pguresvt_destroy(h);
+}
+
 static bool is_pinned(const void *ptr)
 {
     cudaPointerAttributes at{};
@@ -1872,14 +2094,33 @@ static int run_device(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols
                 block = std::min<uint32_t>(block, (uint32_t)atoi(e));
     }
     int rc = PGS_OK;
+    static const bool trace = getenv("PGURESVT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    const auto t_begin = now();
     const uint32_t fe0 = (uint32_t)std::min<uint64_t>((uint64_t)fb + block, std::max(fe, fb));
+    static const bool use_cache = !(getenv("PGURESVT_NO_CACHE") && atoi(getenv("PGURESVT_NO_CACHE")) > 0);
+    pguresvt_handle *h = (use_cache && n_rows == n_cols) ? cache_take(dtype, n_rows, p) : nullptr;
+    if (h)
+    {
+        if (p.random_seed < 0)
+            h->perturbed = false; // fresh entropy per call (pgure.hpp:52-55)
+        if (retarget_impl(h, n_frames, fb, fe0) != PGS_OK)
+        { // too small for this call (or an invalid request: create reports it)
+            pguresvt_destroy(h);
+            h = nullptr;
+        }
+    }
     // (an empty sequence still goes through create once for its error message)
-    pguresvt_handle *h = create_handle(dtype, n_rows, n_cols, n_frames, &p, fb, n_frames ? fe0 : 0, &rc);
+    if (!h)
+        h = create_handle(dtype, n_rows, n_cols, n_frames, &p, fb, n_frames ? fe0 : 0, &rc);
     if (!h)
         return rc ? rc : PGS_ERR_ARG;
+    if (trace)
+        fprintf(stderr, "[pguresvt] device %d frames [%u,%u) sub-block %u: create %.1f ms\n", p.device, fb, fe, block, ms_since(t_begin));
     const bool x_pinned = is_pinned(X);
     // page-locked staging of the input sub-blocks (two buffers: one in use by the device, one being filled)
-    void *stg[2] = {nullptr, nullptr};
+    void **stg = h->stg;
     const size_t stg_bytes = fsz * esz * h->cap_res;
     std::thread stager;
     auto stage = [&](int buf, uint32_t r0, uint32_t r1) { memcpy(stg[buf], (const char *)X + fsz * esz * r0, fsz * esz * (r1 - r0)); };
@@ -1887,10 +2128,18 @@ static int run_device(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols
         r0 = window_start(h, b0);
         r1 = window_start(h, b1 - 1) + h->win;
     };
-    if (!x_pinned)
+    if (!x_pinned && h->stg_bytes < stg_bytes)
+    {
         for (int i = 0; i < 2 && !rc; i++)
+        {
+            if (stg[i])
+                cudaFreeHost(stg[i]);
+            stg[i] = nullptr;
             if (cudaMallocHost(&stg[i], stg_bytes) != cudaSuccess)
                 rc = fail(PGS_ERR_CUDA, "cannot allocate %zu bytes of page-locked staging memory", stg_bytes);
+        }
+        h->stg_bytes = rc ? 0 : stg_bytes;
+    }
     if (!rc)
         rc = pguresvt_stream_output(h, Y);
     int buf = 0;
@@ -1916,6 +2165,7 @@ static int run_device(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols
             resident(n0, n1, r0, r1);
             stager = std::thread(stage, buf ^ 1, r0, r1);
         }
+        const auto t_blk = now();
         if (x_pinned)
             rc = pguresvt_upload(h, X);
         else // pguresvt_upload takes the address frame 0 would have
@@ -1924,14 +2174,21 @@ static int run_device(int dtype, const void *X, uint32_t n_rows, uint32_t n_cols
             rc = pguresvt_process(h);
         if (!rc)
             rc = pguresvt_download(h, nullptr, estimates);
+        if (trace)
+            fprintf(stderr, "[pguresvt] device %d sub-block [%u,%u): %.1f ms (device timeline %.1f ms)\n", p.device, b0, b1, ms_since(t_blk),
+                    h->stats[9]);
     }
     if (stager.joinable())
         stager.join();
     const std::string keep = g_err;
-    pguresvt_destroy(h);
-    for (int i = 0; i < 2; i++)
-        if (stg[i])
-            cudaFreeHost(stg[i]);
+    const auto t_end = now();
+    pguresvt_stream_output(h, nullptr);
+    if (use_cache && rc == PGS_OK)
+        cache_put(h);
+    else
+        pguresvt_destroy(h);
+    if (trace)
+        fprintf(stderr, "[pguresvt] device %d: destroy %.1f ms, total %.1f ms\n", p.device, ms_since(t_end), ms_since(t_begin));
     g_err = keep;
     return rc;
 }
@@ -2121,6 +2378,22 @@ extern "C" int pguresvt_probe_noise(pguresvt_handle *h, uint32_t t, double *alph
         return rc;
     return noise_estimate_window(h->noise_ws, h->dU, (int)h->N, (int)h->win, (int)h->p.noise_method, h->sm_count, h->st, *alpha, *mu,
                                  *sigma, &h->launches, g_err, (long long)h->cur_a, h->cur_uMax);
+}
+
+extern "C" int pguresvt_probe_window_sum(pguresvt_handle *h, uint32_t t, double *sum)
+{
+    CHECK_T(h, t);
+    if (!sum)
+        return fail(PGS_ERR_ARG, "null argument");
+    drop_prelaunched_noise(h);
+    int rc = prefilter(h);
+    if (rc)
+        return rc;
+    h->cur_t = -1;
+    if ((rc = stage_window(h, t)) || (rc = sum_u_launch(h)) || (rc = sum_u_wait(h)))
+        return rc;
+    *sum = h->cur_sumU;
+    return PGS_OK;
 }
 
 extern "C" int pguresvt_device_info(int device, char *name, int len)

@@ -73,6 +73,8 @@ def load():
         fn.argtypes = [vp, u32, u32, u32, pp, dp, dp]
         fn.restype = C.c_int
     L.pguresvt_last_error.restype = C.c_char_p
+    L.pguresvt_release_cached.argtypes = []
+    L.pguresvt_release_cached.restype = None
     L.pguresvt_create.argtypes = [C.c_int, u32, u32, u32, pp, u32, u32]
     L.pguresvt_create.restype = vp
     L.pguresvt_destroy.argtypes = [vp]
@@ -98,6 +100,7 @@ def load():
     L.pguresvt_probe_reconstruct.argtypes = [vp, u32, C.c_double, dp]
     L.pguresvt_probe_perturbations.argtypes = [vp, C.POINTER(C.c_int8), C.POINTER(C.c_int8)]
     L.pguresvt_probe_noise.argtypes = [vp, u32, dp, dp, dp]
+    L.pguresvt_probe_window_sum.argtypes = [vp, u32, dp]
     L.pguresvt_hotpixel_u16.argtypes = [C.POINTER(C.c_uint16), u32, u32, u32, C.c_double, C.c_int]
     L.pguresvt_bench_dfma.argtypes = [C.c_int, dp, dp]
     L.pguresvt_device_info.argtypes = [C.c_int, C.c_char_p, C.c_int]
@@ -117,6 +120,11 @@ def frame_block(n_frames, parts, part):
     b, e = C.c_uint32(0), C.c_uint32(0)
     check(load().pguresvt_host_frame_block(int(n_frames), int(parts), int(part), C.byref(b), C.byref(e)), "frame_block")
     return b.value, e.value
+
+
+def release_cached():
+    """Free the per-device handles the one-shot entry points keep between calls."""
+    load().pguresvt_release_cached()
 
 
 def last_error():
@@ -309,6 +317,11 @@ class Handle:
         a, m, s = C.c_double(alpha), C.c_double(mu), C.c_double(sigma)
         check(self.L.pguresvt_probe_noise(self.h, t, C.byref(a), C.byref(m), C.byref(s)), "probe_noise")
         return a.value, m.value, s.value
+
+    def probe_window_sum(self, t):
+        s = C.c_double(0)
+        check(self.L.pguresvt_probe_window_sum(self.h, t, C.byref(s)), "probe_window_sum")
+        return s.value
 
     def close(self):
         if getattr(self, "h", None):

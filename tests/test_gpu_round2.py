@@ -128,7 +128,7 @@ def test_pgure_pixels_1e6_at_oracle_lambda():
     X = g["X"]
     alpha, mu, sigma = g["pgure_params"]
     est, Yo = g["est_pgure"], g["Y_pgure"]
-    h = bridge.Handle(X, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1)
+    h = bridge.Handle(X, lambda1=-1.0, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1)
     F, fw = X.shape[2], 7
     for t in (0, 5, 8, 15):
         a = 0 if t < fw else (F - 2 * fw - 1 if t >= F - fw else t - fw)
@@ -288,3 +288,64 @@ def test_bench_dfma_peak_is_plausible():
     b, s = C.c_double(0), C.c_double(0)
     assert bridge.load().pguresvt_bench_dfma(0, C.byref(b), C.byref(s)) == 0
     assert 20.0 < s.value <= b.value * 1.02 < 60.0
+
+
+# ------------------------------------------------------------------ start point of the lambda search: accu(u) bit for bit
+def _arma_accu(u):
+    """arma::accu of a cube: two sequential accumulators over the column-major memory (np.cumsum adds sequentially)."""
+    flat = np.asarray(u, dtype=np.float64).ravel(order="F")
+    acc1 = np.cumsum(flat[0::2])[-1]
+    acc2 = np.cumsum(flat[1::2])[-1] if flat.size > 1 else 0.0
+    return acc1 + acc2
+
+
+@pytest.mark.parametrize("case", ["synthetic", "sparse", "saturated", "float32", "odd_size", "ties", "big"])
+def test_window_sum_is_armadillo_accu_bit_for_bit(case):
+    """The search's start point accu(u)/(Nx Ny Nt) (pguresvt.hpp:139) decides which point of the flat basin the search ends
+    on, so the device reproduces Armadillo's sequential two-accumulator sum exactly (k_accu_seq: integer emulation of the
+    running FP64 sum inside a parallel scan)."""
+    rng = np.random.RandomState(3)
+    N, F, t = 64, 17, 8
+    if case == "synthetic":
+        X, _ = synthetic_sequence(N, F, seed=2)
+    elif case == "sparse":
+        X = np.zeros((N, N, F), dtype=np.uint16, order="F")
+        idx = rng.randint(0, X.size, 300)
+        X.ravel(order="K")[idx] = rng.randint(1, 65535, 300)
+    elif case == "saturated":
+        X = np.asfortranarray(rng.randint(0, 4, size=(N, N, F)).astype(np.uint16) * 21845)  # many elements equal to the maximum
+    elif case == "float32":
+        X = np.asfortranarray((rng.rand(N, N, F) * 1000).astype(np.float32))
+    elif case == "odd_size":
+        N = 33
+        X, _ = synthetic_sequence(N, F, seed=4)
+    elif case == "ties":
+        X = np.asfortranarray(rng.randint(0, 2 ** 45, size=(N, N, F)).astype(np.float64) / 2.0 ** 45)
+        X[0, 0, :] = 1.0
+    else:
+        N = 512
+        X, _ = synthetic_sequence(N, F, seed=6)
+    h = bridge.Handle(X, optimize_pgure=True, lambda1=-1.0, noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03, random_seed=1,
+                      frame_begin=t, frame_end=t + 1, motion_estimation=False, motion_filter=-1 if X.dtype.kind == "f" else 5)
+    got = h.probe_window_sum(t)
+    u = X[:, :, t - 7:t + 8].astype(np.float64)
+    u = u / u.max()
+    want = _arma_accu(u)
+    assert got == want, (got, want, got - want)
+    h.close()
+
+
+def test_bench_sample_lambda_matches_oracle_on_every_frame():
+    """With the exact start point the device search follows the oracle's probe for probe: every frame of the bench's CPU
+    sample (128^2 crop, noise estimated) ends on the oracle's lambda, pixels follow to 1e-6."""
+    X, _ = synthetic_sequence(128, 8 + 14, seed=123)
+    kw = dict(trajectory_length=15, patch_size=4, patch_overlap=1, motion_window=7, motion_filter=5, noise_method=4, max_iter=500,
+              random_seed=1, exponential_weighting=True, motion_estimation=True, tol=1e-7, optimize_pgure=True, lambda1=-1.0)
+    Yo, eo = orc.pguresvt(X, n_jobs=os.cpu_count(), frame_begin=7, frame_end=15, **kw)
+    h = bridge.Handle(X, frame_begin=7, frame_end=15, **kw)
+    h.process()
+    Y, e = h.download()
+    h.close()
+    for t in range(7, 15):
+        assert abs(e[t, 0] - eo[t, 0]) / eo[t, 0] < 1e-9, (t, e[t, 0], eo[t, 0])
+        assert np.abs(Y[:, :, t] - Yo[:, :, t]).max() / np.abs(Yo[:, :, t]).max() < PIX_TOL
