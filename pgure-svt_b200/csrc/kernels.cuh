@@ -1191,11 +1191,18 @@ __device__ __forceinline__ void cp_async_wait()
 
 #define SVD16_V0_STRIDE 242 /* doubles per matrix in shared memory: 15 x 16 + 2 padding (bank spread) */
 
-template <int WARM, int TRACK>
+// EPI selects what the epilogue leaves behind:
+//   0  the full record U | V | S (svt.hpp:111-116) — generic consumers, exact fallback of the lean mode;
+//   1  ONLY the head entries of this object: its three largest singular values and the bilinear forms q_k = u_k^T C4 v_k of the
+//      two leading triplets (see k_qform3) — what the lambda search consumes of the perturbed objects U +- eps2*delta2.  No U/V
+//      stores (3,968 B per patch), V rebuilt for two columns instead of fifteen, no separate q-form pass over the records;
+//   2  full record AND head entries (object U: the search rebuilds Uhat from its leading triplets).
+// head: 16 doubles per patch = S0[0..2] | S2[0..2] | S3[0..2] | q0[0..1] | q2[0..1] | q3[0..1] | pad; part = 0, 1, 2 for objects U, U2p, U2m.
+template <int WARM, int TRACK, int EPI>
 __global__ void __launch_bounds__(128, 2)
     k_svd16_l4(const double *__restrict__ u, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
                int vecSize, int N, double *__restrict__ fac, const double *__restrict__ fac0, int max_sweeps, double tol2,
-               double big2, int *__restrict__ sweeps_out)
+               double big2, int *__restrict__ sweeps_out, const double *__restrict__ c4, double *__restrict__ head, int part)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = threadIdx.x & 3; // patch column owned by this lane
@@ -1516,15 +1523,34 @@ __global__ void __launch_bounds__(128, 2)
         }
         if (valid)
         {
-            double2 *dst = reinterpret_cast<double2 *>(R + SVD16_M * rk[j] + 4 * sub);
-            dst[0] = make_double2(uu[0], uu[1]);
-            dst[1] = make_double2(uu[2], uu[3]);
-            if ((j >> 2) == sub)
-                R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + rk[j]] = sig[j];
+            if (EPI != 1)
+            {
+                double2 *dst = reinterpret_cast<double2 *>(R + SVD16_M * rk[j] + 4 * sub);
+                dst[0] = make_double2(uu[0], uu[1]);
+                dst[1] = make_double2(uu[2], uu[3]);
+                if ((j >> 2) == sub)
+                    R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + rk[j]] = sig[j];
+            }
+            if (EPI != 0 && (j >> 2) == sub && rk[j] < 3)
+                head[(size_t)16 * pidx + 3 * part + rk[j]] = sig[j];
         }
     }
-    if (valid && sub == 3)
+    if (EPI != 1 && valid && sub == 3)
         R[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 15] = smax; // slot 15 carries sigma_max
+    // slots and singular values of the two leading triplets (head entries)
+    int lead0 = 0, lead1 = 0;
+    double sl0 = 0.0, sl1 = 0.0;
+    if (EPI != 0)
+    {
+#pragma unroll
+        for (int j = 0; j < SVD16_N; j++)
+        {
+            if (rk[j] == 0)
+                lead0 = j, sl0 = sig[j];
+            if (rk[j] == 1)
+                lead1 = j, sl1 = sig[j];
+        }
+    }
     // V(i, k) = sum_rows A(row, i) * z(row, k).  z is handed over through shared memory (the V0 buffer of the warm start is
     // dead by now; the cold kernel is launched with the same allocation): lane `sub` then owns rows i = 4*sub .. 4*sub+3 of V,
     // re-gathers those four complete columns of A (16 values each) and forms all 15 inner products per column locally —
@@ -1552,35 +1578,125 @@ __global__ void __launch_bounds__(128, 2)
                 ac[ii][4 * c2 + r] = __ldg(u + vox + (size_t)N * c2 + r);
     }
     __syncwarp();
-    double *Vg = R + SVD16_M * SVD16_N;
-#pragma unroll
-    for (int k = 0; k < SVD16_N; k++)
+    // head entries: t_k(i) = sigma_k sum_rows C4(row, i) z_k(row) for the two leading triplets and this lane's four slices;
+    // q_k = sum_i v_k(i) t_k(i) is finished below once v_k(i) is known
+    double t0[4] = {0.0, 0.0, 0.0, 0.0}, t1[4] = {0.0, 0.0, 0.0, 0.0};
+    if (EPI != 0)
     {
-        double zk[16];
+        double z0[16], z1[16];
 #pragma unroll
         for (int h2 = 0; h2 < 8; h2++)
         {
-            const double2 v = reinterpret_cast<const double2 *>(zs + 16 * k)[h2];
-            zk[2 * h2] = v.x;
-            zk[2 * h2 + 1] = v.y;
+            const double2 v0 = reinterpret_cast<const double2 *>(zs + 16 * lead0)[h2];
+            const double2 v1 = reinterpret_cast<const double2 *>(zs + 16 * lead1)[h2];
+            z0[2 * h2] = v0.x, z0[2 * h2 + 1] = v0.y;
+            z1[2 * h2] = v1.x, z1[2 * h2 + 1] = v1.y;
         }
-        double vo[4];
 #pragma unroll
         for (int ii = 0; ii < 4; ii++)
         {
-            double sacc = 0.0;
+            const int i = min(4 * sub + ii, SVD16_N - 1);
+            const short2 p = pos[(size_t)i * vecSize + id];
+            const size_t vox = (size_t)p.x + (size_t)N * p.y + fsz * i;
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int row = 0; row < 16; row++)
-                sacc = fma(ac[ii][row], zk[row], sacc);
-            vo[ii] = sacc;
+            for (int c2 = 0; c2 < 4; c2++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    const double cw = __ldg(c4 + vox + (size_t)N * c2 + r);
+                    s0 = fma(cw, z0[4 * c2 + r], s0);
+                    s1 = fma(cw, z1[4 * c2 + r], s1);
+                }
+            const bool real = 4 * sub + ii < SVD16_N;
+            t0[ii] = real ? s0 * sl0 : 0.0;
+            t1[ii] = real ? s1 * sl1 : 0.0;
         }
-        if (sub == 3)
-            vo[3] = 0.0; // row 15 of V is padding
-        if (valid)
+    }
+    double *Vg = R + SVD16_M * SVD16_N;
+    double q0acc = 0.0, q1acc = 0.0;
+    if (EPI == 1)
+    { // only the two leading columns of V are formed (never stored)
+#pragma unroll 1
+        for (int w2 = 0; w2 < 2; w2++)
         {
-            double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * rk[k] + 4 * sub);
-            dst[0] = make_double2(vo[0], vo[1]);
-            dst[1] = make_double2(vo[2], vo[3]);
+            const int k = w2 ? lead1 : lead0;
+            double zk[16];
+#pragma unroll
+            for (int h2 = 0; h2 < 8; h2++)
+            {
+                const double2 v = reinterpret_cast<const double2 *>(zs + 16 * k)[h2];
+                zk[2 * h2] = v.x;
+                zk[2 * h2 + 1] = v.y;
+            }
+            double vo[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+            {
+                double sacc = 0.0;
+#pragma unroll
+                for (int row = 0; row < 16; row++)
+                    sacc = fma(ac[ii][row], zk[row], sacc);
+                vo[ii] = sacc;
+            }
+            if (sub == 3)
+                vo[3] = 0.0;
+            if (w2 == 0)
+                q0acc = fma(vo[0], t0[0], fma(vo[1], t0[1], fma(vo[2], t0[2], vo[3] * t0[3])));
+            else
+                q1acc = fma(vo[0], t1[0], fma(vo[1], t1[1], fma(vo[2], t1[2], vo[3] * t1[3])));
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < SVD16_N; k++)
+        {
+            double zk[16];
+#pragma unroll
+            for (int h2 = 0; h2 < 8; h2++)
+            {
+                const double2 v = reinterpret_cast<const double2 *>(zs + 16 * k)[h2];
+                zk[2 * h2] = v.x;
+                zk[2 * h2 + 1] = v.y;
+            }
+            double vo[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+            {
+                double sacc = 0.0;
+#pragma unroll
+                for (int row = 0; row < 16; row++)
+                    sacc = fma(ac[ii][row], zk[row], sacc);
+                vo[ii] = sacc;
+            }
+            if (sub == 3)
+                vo[3] = 0.0; // row 15 of V is padding
+            if (EPI != 0)
+            {
+                if (k == lead0)
+                    q0acc = fma(vo[0], t0[0], fma(vo[1], t0[1], fma(vo[2], t0[2], vo[3] * t0[3])));
+                if (k == lead1)
+                    q1acc = fma(vo[0], t1[0], fma(vo[1], t1[1], fma(vo[2], t1[2], vo[3] * t1[3])));
+            }
+            if (valid)
+            {
+                double2 *dst = reinterpret_cast<double2 *>(Vg + SVD16_LDV * rk[k] + 4 * sub);
+                dst[0] = make_double2(vo[0], vo[1]);
+                dst[1] = make_double2(vo[2], vo[3]);
+            }
+        }
+    }
+    if (EPI != 0)
+    {
+        q0acc += __shfl_xor_sync(0xffffffffu, q0acc, 1);
+        q0acc += __shfl_xor_sync(0xffffffffu, q0acc, 2);
+        q1acc += __shfl_xor_sync(0xffffffffu, q1acc, 1);
+        q1acc += __shfl_xor_sync(0xffffffffu, q1acc, 2);
+        if (valid && sub == 0)
+        {
+            head[(size_t)16 * pidx + 9 + 2 * part] = q0acc;
+            head[(size_t)16 * pidx + 9 + 2 * part + 1] = q1acc;
         }
     }
     if (sweeps_out && (threadIdx.x & 31) == 0)
@@ -1773,7 +1889,10 @@ __global__ void __launch_bounds__(128, 8)
     }
 }
 
-template <int MINB, int PPG>
+// LEAN: S and q of the three objects come from the 128-byte head record the SVD kernels leave behind (three singular values
+// and two q-forms per object); a surviving THIRD singular value of any object flags need_more_q and the caller repeats
+// the evaluation through the general path after decomposing the perturbed objects in full.
+template <int MINB, int PPG, int LEAN>
 __global__ void __launch_bounds__(128, MINB)
     k_eval3(const double *__restrict__ fac0, const double *__restrict__ fac2, const double *__restrict__ fac3,
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
@@ -1807,7 +1926,17 @@ __global__ void __launch_bounds__(128, MINB)
             pidx = P - 1;
         const size_t roff = (size_t)SVD16_REC * pidx;
         double *dst = sg + st * EV_STAGE;
-        if (g < 8)
+        if (LEAN)
+        { // head record (q0 carries it in this mode), U and V column 0 of object U
+            if (g < 8)
+            {
+                cp_async16(dst + 0 + 2 * g, q0 + (size_t)16 * pidx + 2 * g);
+                cp_async16(dst + 96 + 2 * g, fac0 + roff + 2 * g);
+            }
+            else
+                cp_async16(dst + 112 + 2 * (g - 8), fac0 + roff + SVD16_M * SVD16_N + 2 * (g - 8));
+        }
+        else if (g < 8)
         { // S of the three objects, U column 0
             cp_async16(dst + 0 + 2 * g, fac0 + roff + soff + 2 * g);
             cp_async16(dst + 16 + 2 * g, fac2 + roff + soff + 2 * g);
@@ -1851,7 +1980,20 @@ __global__ void __launch_bounds__(128, MINB)
         const double *ss = sg + st * EV_STAGE;
         const short2 *sp = reinterpret_cast<const short2 *>(ss + 128);
         double f0 = 0.0, s4 = 0.0;
-        if (g < SVD16_N)
+        if (LEAN)
+        {
+            if (g < 3)
+            {
+                f0 = soft_f(ss[g], ss[0], lambda, expw);
+                const double f2 = soft_f(ss[3 + g], ss[3], lambda, expw);
+                const double f3 = soft_f(ss[6 + g], ss[6], lambda, expw);
+                if (g < 2)
+                    s4 = fma(f2, ss[11 + g], fma(f3, ss[13 + g], -2.0 * f0 * ss[9 + g]));
+                else if ((f0 != 0.0 || f2 != 0.0 || f3 != 0.0) && valid)
+                    *need_more_q = 1;
+            }
+        }
+        else if (g < SVD16_N)
         {
             f0 = soft_f(ss[g], ss[15], lambda, expw);
             const double f2 = soft_f(ss[16 + g], ss[16 + 15], lambda, expw);

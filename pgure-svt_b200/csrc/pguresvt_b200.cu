@@ -78,11 +78,14 @@ struct pguresvt_handle
     bool use_reg_svd = false; // any register-resident 16x15 kernel
     bool use_l4 = false;      // 4-lanes-per-matrix kernel (S in slot order, S[15] = sigma_max)
     bool use_fused_eval = false;
+    bool lean = false;           // fused path: perturbed objects leave only head entries behind (k_svd16_l4 EPI 1), no q-form pass
+    bool frame_full = false;     // lean mode: the current frame has been decomposed in full after all (a third triplet survived)
+    bool full_mode = false;      // stage_svd: write full records for the perturbed objects (fallback of the lean mode, probes)
     bool use_tile = false;       // atomics-free gather evaluation (tile_eval.cuh) on top of the fused path
     bool frame_fallback = false; // a third triplet survived at some probe of this frame: general k_eval3 path from there on
     int *dBinCnt = nullptr, *dBinStart = nullptr, *dScanSums = nullptr;
     TgEntry *dEnt = nullptr;
-    double *dHead = nullptr, *dTilePart = nullptr;
+    double *dHead = nullptr, *dTilePart = nullptr, *dU0c = nullptr;
     double2 *dFth = nullptr;
     int tile_r = 0, tile_c = 0;
     // arma::accu(u) bit for bit (k_accu_seq) on its own stream beside the ARPS / SVD stages
@@ -286,7 +289,7 @@ static void free_all(pguresvt_handle *h)
     if (h->hSum2)
         cudaFreeHost(h->hSum2);
     F(h->dSum2);
-    F(h->dBinCnt), F(h->dBinStart), F(h->dScanSums), F(h->dEnt), F(h->dHead), F(h->dTilePart), F(h->dFth);
+    F(h->dBinCnt), F(h->dBinStart), F(h->dScanSums), F(h->dEnt), F(h->dHead), F(h->dTilePart), F(h->dFth), F(h->dU0c);
     if (h->hOvf)
         cudaFreeHost(h->hOvf);
     F(h->dD1), F(h->dD2), F(h->dC4), F(h->dPartialE), F(h->dKpart), F(h->dQ[0]), F(h->dQ[1]), F(h->dQ[2]), F(h->dPartial), F(h->dOut), F(h->dMaxPartial), F(h->dY), F(h->dEst), F(h->dV), F(h->dSweeps),
@@ -379,6 +382,7 @@ static int create_impl(pguresvt_handle *h)
         return fail(PGS_ERR_UNSUPPORTED, "register SVD kernels only cover 16x15 Casorati matrices");
     h->use_l4 = h->use_reg_svd && p.svd_kernel != 2; // 0 / 3: 4-lane kernel with tracked / recomputed pair norms
     h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
+    h->lean = h->use_fused_eval && !(getenv("PGURESVT_LEAN") && atoi(getenv("PGURESVT_LEAN")) == 0);
     h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
     // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
     h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
@@ -399,10 +403,10 @@ static int create_impl(pguresvt_handle *h)
       // the generic shared-memory SVD — slower, but it runs (default-parameter sequences at 4096^2).
         size_t freeb = 0, totb = 0;
         CU(cudaMemGetInfo(&freeb, &totb));
-        const size_t need = h->rec * (size_t)h->P * sizeof(double) * h->nobj + wtot * 60 + h->fsz * ((size_t)nres * (h->esz + 2) + (size_t)nblk * 8);
+        const size_t need = h->rec * (size_t)h->P * sizeof(double) * (h->lean ? 1 : h->nobj) + wtot * 60 + h->fsz * ((size_t)nres * (h->esz + 2) + (size_t)nblk * 8);
         if (need > freeb - freeb / 10)
         {
-            h->use_l4 = h->use_reg_svd = h->use_fused_eval = false;
+            h->use_l4 = h->use_reg_svd = h->use_fused_eval = h->lean = false;
             h->use_compact = p.eps1_mode == 0;
             if (!h->use_compact)
                 return fail(PGS_ERR_UNSUPPORTED, "the SVD factors of %d patches x %d objects (%.1f GB) do not fit on device %d (%.1f GB free)", h->P,
@@ -462,6 +466,8 @@ static int create_impl(pguresvt_handle *h)
             CU(cudaMemset(h->dQc[o], 0, (size_t)32 * h->P * sizeof(double)));
             continue;
         }
+        if (h->lean && o != 0)
+            continue; // perturbed objects leave head entries only; full records on demand (stage_svd)
         CU(cudaMalloc(&h->dFac[o], h->rec * (size_t)h->P * sizeof(double)));
         CU(cudaMemset(h->dFac[o], 0, h->rec * (size_t)h->P * sizeof(double)));
     }
@@ -481,9 +487,15 @@ static int create_impl(pguresvt_handle *h)
         CU(cudaMalloc(&h->dPartialE, ((size_t)4 * h->eval_blocks + 64) * sizeof(double)));
         CU(cudaMalloc(&h->dKpart, ((size_t)4 * h->eval_blocks + 64) * sizeof(int)));
 
-        for (int k = 0; k < 3; k++)
-            CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
-        h->use_tile = !(getenv("PGURESVT_TILE_EVAL") && atoi(getenv("PGURESVT_TILE_EVAL")) == 0);
+        if (!h->lean)
+            for (int k = 0; k < 3; k++)
+                CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
+        CU(cudaMalloc(&h->dHead, (size_t)TG_HEAD * h->P * sizeof(double)));
+        CU(cudaMemset(h->dHead, 0, (size_t)TG_HEAD * h->P * sizeof(double)));
+        // the atomics-free gather evaluation (tile_eval.cuh) is exact and deterministic too, but on B200 its irregular gather costs
+        // more instructions than the L2 atomic unit costs time: 1.0 ms against 0.55 ms per evaluation at 1024^2 (profiles/r02) —
+        // opt-in with PGURESVT_TILE_EVAL=1
+        h->use_tile = getenv("PGURESVT_TILE_EVAL") && atoi(getenv("PGURESVT_TILE_EVAL")) > 0;
         if (h->use_tile)
         {
             const size_t nbins = h->fsz * h->win;
@@ -492,7 +504,7 @@ static int create_impl(pguresvt_handle *h)
             CU(cudaMalloc(&h->dBinStart, (nbins + 1) * sizeof(int)));
             CU(cudaMalloc(&h->dScanSums, ((size_t)cdiv(nbins, SCAN_ITEMS) + 1) * sizeof(int)));
             CU(cudaMalloc(&h->dEnt, (size_t)h->P * h->win * sizeof(TgEntry)));
-            CU(cudaMalloc(&h->dHead, (size_t)TG_HEAD * h->P * sizeof(double)));
+            CU(cudaMalloc(&h->dU0c, (size_t)16 * h->P * sizeof(double)));
             CU(cudaMalloc(&h->dFth, (size_t)h->P * sizeof(double2)));
             CU(cudaMalloc(&h->dTilePart, (size_t)2 * h->tile_r * h->tile_c * h->win * sizeof(double)));
         }
@@ -1187,8 +1199,18 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         //  the instruction cache: measured 1.15x (3 rounds) to 1.7x (15 rounds) slower on B200)
         // 4: tracked norms with full rotations; 0 (default): tracked norms with fast (scaled) rotations
         const int variant = h->p.svd_kernel == 3 ? 0 : h->p.svd_kernel == 4 ? 1 : 2;
-        auto cold = variant == 2 ? k_svd16_l4<0, 2> : variant == 1 ? k_svd16_l4<0, 1> : k_svd16_l4<0, 0>;
-        auto warm = variant == 2 ? k_svd16_l4<1, 2> : variant == 1 ? k_svd16_l4<1, 1> : k_svd16_l4<1, 0>;
+        // epilogue: lean mode leaves head entries (+ the full record of object U); see k_svd16_l4
+        const int epi = !h->lean ? 0 : (obj == 0 ? 2 : (h->full_mode ? 0 : 1));
+        auto cold = epi == 2 ? (variant == 2 ? k_svd16_l4<0, 2, 2> : variant == 1 ? k_svd16_l4<0, 1, 2> : k_svd16_l4<0, 0, 2>)
+                             : (variant == 2 ? k_svd16_l4<0, 2, 0> : variant == 1 ? k_svd16_l4<0, 1, 0> : k_svd16_l4<0, 0, 0>);
+        auto warm = epi == 1 ? (variant == 2 ? k_svd16_l4<1, 2, 1> : variant == 1 ? k_svd16_l4<1, 1, 1> : k_svd16_l4<1, 0, 1>)
+                             : (variant == 2 ? k_svd16_l4<1, 2, 0> : variant == 1 ? k_svd16_l4<1, 1, 0> : k_svd16_l4<1, 0, 0>);
+        const int part = obj == 0 ? 0 : obj == 2 ? 1 : 2;
+        if (epi == 0 && obj != 0 && !h->dFac[obj])
+        { // full records of a perturbed object in lean mode: allocated on first use (4 GB per object at 1024^2)
+            CU(cudaMalloc(&h->dFac[obj], h->rec * (size_t)h->P * sizeof(double)));
+            CU(cudaMemsetAsync(h->dFac[obj], 0, h->rec * (size_t)h->P * sizeof(double), h->st));
+        }
         const double *usrc = h->dU;
         if (obj != 0)
         { // U + eps*delta written out once (pgure.hpp:80-82); the SVD kernel then gathers plain doubles
@@ -1199,18 +1221,14 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         }
         // dynamic shared memory: V of object 0 for the warm start, re-used for the hand-over of z in the V rebuild (both variants)
         const int smem_svd = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
-        if (!h->attr_warm)
-        { // per device: the handle is bound to one device
-            CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
-            CU(cudaFuncSetAttribute(cold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
-            h->attr_warm = true;
-        }
+        // (the attribute is per function: set it for the instance about to be launched)
+        CU(cudaFuncSetAttribute(obj == 0 ? cold : warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
         if (obj == 0)
             cold<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
-                                                                max_sweeps, tol2, big2, h->dSweeps);
+                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
             warm<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], h->dFac[0],
-                                                                max_sweeps, tol2, big2, h->dSweeps);
+                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part);
     }
     else if (h->use_reg_svd)
     {
@@ -1438,6 +1456,32 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
     return launch_recon_generic(h, h->dFac[obj], h->dIds, h->P, lambda, only_k, h->dAcc[obj]);
 }
 
+// Lean mode, exact fallback: a third singular triplet of some object survived at the probed lambda (or a probe asks for the
+// factors of a perturbed object).  The perturbed objects are decomposed again with full records, all q-forms are prepared
+// and the rest of the frame runs through the general evaluation.
+static int ensure_full(pguresvt_handle *h)
+{
+    if (!h->lean || h->frame_full)
+        return PGS_OK;
+    int rc;
+    h->full_mode = true;
+    for (int obj = 2; obj <= 3; obj++)
+        if ((rc = stage_svd(h, obj)))
+        {
+            h->full_mode = false;
+            return rc;
+        }
+    h->full_mode = false;
+    for (int k = 0; k < 3; k++)
+        if (!h->dQ[k])
+            CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
+    if ((rc = launch_qform(h, SVD16_N)))
+        return rc;
+    h->frame_full = true;
+    h->stats[18] += 1;
+    return PGS_OK;
+}
+
 // One evaluation of PGURE::CalculatePGURE (pgure.hpp:120-137).  (alpha, mu, sigma) are the PGURE object's
 // members, i.e. AFTER the sigma/mu swap of pguresvt.hpp:133.
 static int objective_fused(pguresvt_handle *h, double lambda, double alpha, double mu, double sigma, double *value, double *terms)
@@ -1451,10 +1495,13 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     for (int attempt = 0; attempt < 2; attempt++)
     {
         static const int ppg = getenv("PGURESVT_EVAL_PPG") ? atoi(getenv("PGURESVT_EVAL_PPG")) : EVAL_PPG;
-        auto kev = (ppg == 1) ? k_eval3<6, 1> : (ppg == 4) ? k_eval3<6, 4> : (ppg == 16) ? k_eval3<6, 16> : (ppg == 32) ? k_eval3<6, 32> : k_eval3<6, 8>;
-        const int ppg_eff = (ppg == 1 || ppg == 4 || ppg == 16 || ppg == 32) ? ppg : 8;
-        kev<<<cdiv(h->P, 8 * ppg_eff), 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->dPos,
-                                                        h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
+        const bool lean_now = h->lean && !h->frame_full;
+        auto kev = lean_now ? k_eval3<6, 8, 1>
+                            : (ppg == 1) ? k_eval3<6, 1, 0> : (ppg == 4) ? k_eval3<6, 4, 0> : (ppg == 16) ? k_eval3<6, 16, 0> : (ppg == 32) ? k_eval3<6, 32, 0> : k_eval3<6, 8, 0>;
+        const int ppg_eff = lean_now ? 8 : (ppg == 1 || ppg == 4 || ppg == 16 || ppg == 32) ? ppg : 8;
+        // (lean: the head records travel in the q0 argument; fac2/fac3/q2/q3 are not read)
+        kev<<<cdiv(h->P, 8 * ppg_eff), 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], lean_now ? h->dHead : h->dQ[0], h->dQ[1], h->dQ[2],
+                                                        h->dPos, h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
                                                         h->p.exp_weighting, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
         LAUNCHED(h);
         k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
@@ -1467,11 +1514,19 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
         h->stats[16] += h->hOut[3]; // singular triplets streamed by this pass (algorithmic-bytes accounting for bench.py)
         if (!*reinterpret_cast<const int *>(h->hOut + 4))
             break;
-        // a triplet beyond the lazily prepared q-forms survived at this lambda: prepare all of them and redo the pass
-        int rc = launch_qform(h, SVD16_N);
-        if (rc)
-            return rc;
-        h->stats[18] += 1;
+        // a triplet beyond the prepared q-forms survived at this lambda: prepare all of them and redo the pass
+        int rc;
+        if (h->lean)
+        {
+            if ((rc = ensure_full(h)))
+                return rc;
+        }
+        else
+        {
+            if ((rc = launch_qform(h, SVD16_N)))
+                return rc;
+            h->stats[18] += 1;
+        }
     }
     const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
     const double sigmasq = sigma * sigma;
@@ -1509,7 +1564,7 @@ static int tile_prepare(pguresvt_handle *h)
     k_bin_sort<<<std::min(cdiv(nbins, 256), h->sm_count * 32), 256, 0, h->st>>>(h->dBinStart, nbins, h->dEnt);
     LAUNCHED(h);
     k_head_pack<<<cdiv((long long)h->P * 4, 256), 256, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], h->dQ[0], h->dQ[1], h->dQ[2], h->P,
-                                                                     h->dHead);
+                                                                     h->lean ? nullptr : h->dHead, h->dU0c);
     LAUNCHED(h);
     CU(cudaGetLastError());
     h->frame_fallback = false;
@@ -1527,8 +1582,8 @@ static int objective_tile(pguresvt_handle *h, double lambda, double alpha, doubl
     const int nw = cdiv(h->P, 32), ntile = h->tile_r * h->tile_c * (int)h->win;
     k_thresh<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, h->p.exp_weighting, h->dFth, h->dPartialE, h->dKpart, h->dNeedQ);
     LAUNCHED(h);
-    k_tile_eval<0><<<dim3(h->tile_r, h->tile_c, h->win), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dFth, h->dU, h->dCnt, h->N, 0, 1.0,
-                                                                          nullptr, h->dTilePart);
+    k_tile_eval<0><<<dim3(h->win, h->tile_r, h->tile_c), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dU0c, h->dFth, h->dU, h->dCnt, h->N,
+                                                                          0, 1.0, nullptr, h->dTilePart);
     LAUNCHED(h);
     k_reduce_eval<<<1, 1024, 0, h->st>>>(h->dTilePart, ntile, h->dPartialE, h->dKpart, nw, h->dOut);
     LAUNCHED(h);
@@ -1536,10 +1591,16 @@ static int objective_tile(pguresvt_handle *h, double lambda, double alpha, doubl
     CU(cudaStreamSynchronize(h->st));
     if (*reinterpret_cast<const int *>(h->hOut + 4))
     { // a third triplet of some object survived at this lambda: all q-forms, general evaluation for the rest of the frame
-        int rc = launch_qform(h, SVD16_N);
+        int rc;
+        if (h->lean)
+            rc = ensure_full(h);
+        else
+        {
+            rc = launch_qform(h, SVD16_N);
+            h->stats[18] += 1;
+        }
         if (rc)
             return rc;
-        h->stats[18] += 1;
         h->frame_fallback = true;
         return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
     }
@@ -1737,9 +1798,12 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
         }
     }
     if (h->use_fused_eval)
-    { // bilinear forms q = u^T C4 v of the leading singular triplets of the three objects (the rest lazily, see objective_fused)
+    {
         StageTimer tm(h, 17);
-        if ((rc = launch_qform(h, QFORM_LAZY_K)))
+        h->frame_full = false;
+        if (h->lean) // the SVD kernels left the head entries (S, leading q-forms) behind: nothing to prepare
+            CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st));
+        else if ((rc = launch_qform(h, QFORM_LAZY_K))) // q = u^T C4 v of the leading triplets (the rest lazily, see objective_fused)
             return rc;
         if (h->use_tile && (rc = tile_prepare(h)))
             return rc;
@@ -1860,8 +1924,8 @@ static int process_frame(pguresvt_handle *h, uint32_t t) // pgureFunc, pguresvt.
           // than two triplets, and the final lambda is one of the probes)
             k_thresh<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, p.exp_weighting, h->dFth, h->dPartialE, h->dKpart, h->dNeedQ);
             LAUNCHED(h);
-            k_tile_eval<1><<<dim3(h->tile_r, h->tile_c, 1), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dFth, h->dU, h->dCnt, h->N,
-                                                                             h->cur_sl, h->cur_uMax, h->dY + h->fsz * lt, nullptr);
+            k_tile_eval<1><<<dim3(1, h->tile_r, h->tile_c), 128, 0, h->st>>>(h->dBinStart, h->dEnt, h->dFac[0], h->dU0c, h->dFth, h->dU, h->dCnt,
+                                                                             h->N, h->cur_sl, h->cur_uMax, h->dY + h->fsz * lt, nullptr);
             LAUNCHED(h);
         }
         else
@@ -2292,10 +2356,13 @@ extern "C" int pguresvt_probe_arps(pguresvt_handle *h, uint32_t t, int32_t *patc
 extern "C" int pguresvt_probe_singular_values(pguresvt_handle *h, uint32_t t, int obj, double *S, int64_t *n_patches)
 {
     CHECK_T(h, t);
-    if (obj < 0 || obj > 3 || !(h->dFac[obj] || h->dSc[obj]))
+    const bool lean_obj = h->lean && (obj == 2 || obj == 3);
+    if (obj < 0 || obj > 3 || !(h->dFac[obj] || h->dSc[obj] || lean_obj))
         return fail(PGS_ERR_ARG, "SVT object %d not present in this configuration", obj);
     int rc = prepare_frame(h, t);
     if (rc)
+        return rc;
+    if (lean_obj && (rc = ensure_full(h))) // the lean mode keeps no factors of the perturbed objects: decompose them in full
         return rc;
     if (n_patches)
         *n_patches = h->P;

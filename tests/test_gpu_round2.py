@@ -349,3 +349,36 @@ def test_bench_sample_lambda_matches_oracle_on_every_frame():
     for t in range(7, 15):
         assert abs(e[t, 0] - eo[t, 0]) / eo[t, 0] < 1e-9, (t, e[t, 0], eo[t, 0])
         assert np.abs(Y[:, :, t] - Yo[:, :, t]).max() / np.abs(Yo[:, :, t]).max() < PIX_TOL
+
+
+def test_gather_evaluation_matches_the_red_path(monkeypatch):
+    """tile_eval.cuh (opt-in, PGURESVT_TILE_EVAL=1): the atomics-free gather evaluation gives the same objective, lambda
+    and pixels as the fixed-point RED path and as the oracle's goldens."""
+    g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    X = g["X"]
+    alpha, mu, sigma = g["pgure_params"]
+    kw = dict(optimize_pgure=True, lambda1=-1.0, noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PGURESVT_TILE_EVAL", mode)
+        h = bridge.Handle(X, **kw)
+        vals, terms = h.probe_pgure(8, alpha, mu, sigma, g["pgure_lambdas"])
+        h.process()
+        Y, e = h.download()
+        out[mode] = (vals, terms, Y, e)
+        h.close()
+    assert np.abs(out["1"][0] - g["pgure_values"]).max() <= 1e-9 * np.abs(g["pgure_values"]).max()
+    assert np.allclose(out["1"][1], g["pgure_terms"], rtol=1e-7, atol=1e-9)
+    assert np.abs(out["1"][0] - out["0"][0]).max() <= 1e-12 * np.abs(out["0"][0]).max()
+    assert np.abs(out["1"][3][:, 0] - out["0"][3][:, 0]).max() <= 1e-9 * out["0"][3][:, 0].max()
+    assert np.abs(out["1"][2] - out["0"][2]).max() <= 1e-9 * np.abs(out["0"][2]).max()
+    # a probe at which a third triplet survives goes through the general path and comes back exact
+    monkeypatch.setenv("PGURESVT_TILE_EVAL", "1")
+    h = bridge.Handle(X, **kw)
+    v1, _ = h.probe_pgure(8, alpha, mu, sigma, [1e-4, 0.3])
+    h.close()
+    monkeypatch.setenv("PGURESVT_TILE_EVAL", "0")
+    h = bridge.Handle(X, **kw)
+    v0, _ = h.probe_pgure(8, alpha, mu, sigma, [1e-4, 0.3])
+    h.close()
+    assert np.abs(v1 - v0).max() <= 1e-12 * np.abs(v0).max()
