@@ -155,7 +155,9 @@ int pguresvt_download(pguresvt_handle *h, double *Y_full, double *estimates_full
  *  [18] evaluations redone because a triplet beyond the lazily prepared q-forms survived
  *  [19] optimiser probes answered from the per-frame memo (a lambda already evaluated bit for bit)
  *  [20] patches re-decomposed because more than rank_cache triplets survived a probe (compact cache; [18] counts those probes)
- *  [21] leading triplets of object U kept per patch by the compact cache (0: full factor cache) */
+ *  [21] leading triplets of object U kept per patch by the compact cache (0: full factor cache)
+ *  [22] probes beyond the frame's critical lambda that ran the bound check of the lean (dominant-triplet) mode;
+ *  [23] patch SVDs redone exactly because a bound survived the threshold there ([20] counts the patches) */
 #define PGS_NSTATS 24
 int pguresvt_get_stats(const pguresvt_handle *h, double *stats);
 

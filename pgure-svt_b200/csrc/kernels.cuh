@@ -1202,14 +1202,17 @@ template <int WARM, int TRACK, int EPI>
 __global__ void __launch_bounds__(128, 2)
     k_svd16_l4(const double *__restrict__ u, const short2 *__restrict__ pos, const int *__restrict__ ids, int P,
                int vecSize, int N, double *__restrict__ fac, const double *__restrict__ fac0, int max_sweeps, double tol2,
-               double big2, int *__restrict__ sweeps_out, const double *__restrict__ c4, double *__restrict__ head, int part)
+               double big2, int *__restrict__ sweeps_out, const double *__restrict__ c4, double *__restrict__ head, int part,
+               const int *__restrict__ plist = nullptr)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = threadIdx.x & 3; // patch column owned by this lane
     int pidx = gtid >> 2;
-    const bool valid = pidx < P;
+    const bool valid = pidx < P; // P = number of matrices of this launch
     if (!valid)
         pidx = P - 1;
+    if (plist) // the launch walks a list of patch indices (exact re-decomposition of a few patches)
+        pidx = plist[pidx];
     const int id = ids[pidx];
     const size_t fsz = (size_t)N * N;
     extern __shared__ __align__(16) double sv0[]; // WARM: V of object 0 for the block's 32 matrices
@@ -1704,6 +1707,239 @@ __global__ void __launch_bounds__(128, 2)
         atomicMax(sweeps_out, sweep);
         atomicAdd(sweeps_out + 1, sweep);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K_top1 — the perturbed objects U +- eps2*delta2 of the lean PGURE path (pgure.hpp:81-82,136).  The lambda search consumes of
+// them: the thresholded spectrum (through the second-difference sum) and the q-forms of the surviving triplets.  With the
+// reference's exponential weighting (and on Poisson-like data in general) ONE triplet survives at the probed lambdas, so the
+// full 16x15 SVD (~100 Jacobi rounds) is replaced by
+//   * the dominant triplet by power iteration on A^T A, started from object U's v_1 (the perturbation is ~1 % of the data):
+//     sigma_1, u_1, v_1 to full FP64 accuracy, and its q-form u_1^T C4 v_1;
+//   * a RIGOROUS upper bound on every other singular value (Weyl):  sigma_k(A + E) <= sigma_2(A) + ||E||_F for k >= 2, with
+//     sigma_2(A) from object U's exact spectrum and ||E||_F = eps2 * sqrt(sum delta2^2) over the patch's 240 entries.
+// The head record gets S = (sigma_1, bound, -1): the -1 marks "S[1] is a bound".  At a probe where the bound survives the
+// threshold (k_lean_check) — or if the iteration did not converge — the patch is decomposed exactly by k_svd16_l4 before the
+// evaluation, so every probe is answered exactly (soft_f is monotone in s: a bound that does not survive proves that no
+// singular value below it does).  4 lanes per matrix like k_svd16_l4.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2)
+    k_top1_l4(const double *__restrict__ u, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
+              const double *__restrict__ fac0, const int8_t *__restrict__ d2neg, double eps2, double dNeg, double dPos,
+              const double *__restrict__ c4, double *__restrict__ head, int part, int max_iters, int *__restrict__ iters_out)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & 3;
+    int pidx = gtid >> 2;
+    const bool valid = pidx < P;
+    if (!valid)
+        pidx = P - 1;
+    const int id = ids[pidx];
+    const size_t fsz = (size_t)N * N;
+    double a[4][SVD16_N];
+    int nneg = 0;
+#pragma unroll
+    for (int k = 0; k < SVD16_N; k++)
+    {
+        const short2 p = pos[(size_t)k * vecSize + id];
+        const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * k;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            a[r][k] = __ldg(u + vox + r);
+            nneg += d2neg[vox + r] ? 1 : 0;
+        }
+    }
+    const double *R0 = fac0 + (size_t)SVD16_REC * pidx;
+    double x[SVD16_N];
+    double xn2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < SVD16_N; j++)
+    {
+        x[j] = R0[SVD16_M * SVD16_N + j]; // v_1 of object U
+        xn2 = fma(x[j], x[j], xn2);
+    }
+    if (!(xn2 > 0.5))
+    { // rank-deficient object U (zero patch): start from the constant vector
+#pragma unroll
+        for (int j = 0; j < SVD16_N; j++)
+            x[j] = 0.2581988897471611; // 1 / sqrt(15)
+    }
+    // shifted iteration x <- (A^T A - mu) x with mu at the centre of object U's unwanted spectrum [sigma_15^2, sigma_2^2]:
+    // contraction (sigma_2^2 - sigma_15^2) / (2 sigma_1^2 - sigma_2^2 - sigma_15^2) per step instead of (sigma_2 / sigma_1)^2
+    // (the shift only steers convergence; sigma_1 and u_1 come from the final A v_1)
+    double mu_shift = 0.0;
+    {
+        const double *S0 = R0 + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+        mu_shift = 0.5 * (S0[1] * S0[1] + S0[14] * S0[14]);
+        if (!(mu_shift < 0.25 * S0[0] * S0[0]))
+            mu_shift = 0.0;
+    }
+    int it = 0;
+    bool conv = false;
+    double y[4];
+#pragma unroll 1
+    for (; it < max_iters; it++)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < SVD16_N; j += 3)
+            {
+                s0 = fma(a[r][j], x[j], s0);
+                s1 = fma(a[r][j + 1], x[j + 1], s1);
+                s2 = fma(a[r][j + 2], x[j + 2], s2);
+            }
+            y[r] = (s0 + s1) + s2;
+        }
+        double z[SVD16_N], n2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SVD16_N; j++)
+        {
+            double t = fma(a[0][j], y[0], fma(a[1][j], y[1], fma(a[2][j], y[2], a[3][j] * y[3])));
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t = fma(-mu_shift, x[j], t);
+            z[j] = t;
+            n2 = fma(t, t, n2);
+        }
+        if (!(n2 > 0.0))
+        { // zero matrix: nothing to iterate on
+            conv = true;
+        }
+        else if (!conv)
+        {
+            const double inv = rsqrt(n2);
+            double diff = 0.0;
+#pragma unroll
+            for (int j = 0; j < SVD16_N; j++)
+            {
+                const double xn = z[j] * inv;
+                diff = fmax(diff, fabs(xn - x[j]));
+                x[j] = xn;
+            }
+            conv = diff <= 1.0e-15;
+        }
+        if (__all_sync(0xffffffffu, conv))
+            break;
+    }
+    // final pass with the converged v_1: sigma_1 = ||A v_1||, u_1 = A v_1 / sigma_1
+    double s2sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SVD16_N; j += 3)
+        {
+            s0 = fma(a[r][j], x[j], s0);
+            s1 = fma(a[r][j + 1], x[j + 1], s1);
+            s2 = fma(a[r][j + 2], x[j + 2], s2);
+        }
+        y[r] = (s0 + s1) + s2;
+        s2sum = fma(y[r], y[r], s2sum);
+    }
+    s2sum += __shfl_xor_sync(0xffffffffu, s2sum, 1);
+    s2sum += __shfl_xor_sync(0xffffffffu, s2sum, 2);
+    const double sig1 = sqrt(s2sum);
+    const double isig = sig1 > 0.0 ? 1.0 / sig1 : 0.0;
+    // q-form u_1^T C4 v_1 (C4 gathered along the trajectory, the same voxels as the matrix)
+    double qf = 0.0;
+    {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < SVD16_N; k++)
+        {
+            const short2 p = pos[(size_t)k * vecSize + id];
+            const size_t vox = (size_t)p.x + (size_t)N * (p.y + sub) + fsz * k;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                t[r] = fma(__ldg(c4 + vox + r), x[k], t[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            qf = fma(t[r], y[r] * isig, qf);
+    }
+    qf += __shfl_xor_sync(0xffffffffu, qf, 1);
+    qf += __shfl_xor_sync(0xffffffffu, qf, 2);
+    nneg += __shfl_xor_sync(0xffffffffu, nneg, 1);
+    nneg += __shfl_xor_sync(0xffffffffu, nneg, 2);
+    if (valid && sub == 0)
+    {
+        const double e2 = (double)nneg * dNeg * dNeg + (double)(SVD16_M * SVD16_N - nneg) * dPos * dPos;
+        const double s2u = R0[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 1]; // sigma_2 of object U
+        double bound = (s2u + eps2 * sqrt(e2)) * (1.0 + 1e-12);
+        if (!conv)
+            bound = INFINITY; // not converged within max_iters (dominant pair not separated): exact decomposition on first use
+        double *hd = head + (size_t)16 * pidx;
+        hd[3 * part] = sig1;
+        hd[3 * part + 1] = bound;
+        hd[3 * part + 2] = -1.0;
+        hd[9 + 2 * part] = qf;
+        hd[9 + 2 * part + 1] = 0.0;
+    }
+    if (iters_out && (threadIdx.x & 31) == 0)
+    {
+        atomicMax(iters_out, it + 1);
+        atomicAdd(iters_out + 1, it + 1);
+    }
+}
+
+// Lean path, per frame: the lambda beyond which (exponential weighting) / below which (plain thresholding) the first bound of
+// a marked head record survives the threshold — probes on the safe side of it need no check at all.
+//   exponential weighting: f(B) > 0  <=>  B > s1 exp(-lambda B^2 / 2)  <=>  lambda > 2 ln(s1 / B) / B^2;  out[0] = min over patches
+//   plain:                 f(B) > 0  <=>  lambda < B;                                                    out[1] = max over patches
+// out must be preset to {+inf, 0}; doubles >= 0 order like their bit patterns, so atomicMin/Max on the bits is exact.
+__global__ void k_lean_crit(const double *__restrict__ head, int P, double *__restrict__ out)
+{
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    double lmin = INFINITY, bmax = 0.0;
+    if (pidx < P)
+    {
+        const double *hd = head + (size_t)16 * pidx;
+#pragma unroll
+        for (int part = 1; part <= 2; part++)
+            if (hd[3 * part + 2] < 0.0)
+            {
+                const double s1 = hd[3 * part], B = hd[3 * part + 1];
+                bmax = fmax(bmax, B);
+                double lc = 0.0; // B >= s1 or B not finite: survives at any lambda
+                if (B < s1 && B > 0.0)
+                    lc = 2.0 * log(s1 / B) / (B * B) * (1.0 - 1e-9);
+                else if (B <= 0.0)
+                    lc = INFINITY;
+                lmin = fmin(lmin, lc);
+            }
+    }
+    lmin = -warp_max(-lmin);
+    bmax = warp_max(bmax);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMin(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(fmax(lmin, 0.0)));
+        atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(fmin(bmax, 1.7e308)));
+    }
+}
+
+// Lean path, per probe beyond the critical lambda: patches whose bound survives at this lambda -> list (list[0] = count)
+__global__ void k_lean_check(const double *__restrict__ head, int P, double lambda, int expw, int *__restrict__ list)
+{
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= P)
+        return;
+    const double *hd = head + (size_t)16 * pidx;
+    bool off = false;
+#pragma unroll
+    for (int part = 1; part <= 2; part++)
+        if (hd[3 * part + 2] < 0.0)
+        {
+            const double s1 = hd[3 * part], B = hd[3 * part + 1];
+            const double w = expw ? fabs(s1 * exp(-0.5 * lambda * (B * B))) : lambda;
+            off = off || !(B - w <= 0.0);
+        }
+    if (off)
+        list[1 + atomicAdd(list, 1)] = pidx;
 }
 
 // ------------------------------------------------------------------------------------------------------

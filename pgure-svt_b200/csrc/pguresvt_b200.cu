@@ -80,6 +80,12 @@ struct pguresvt_handle
     bool use_fused_eval = false;
     bool lean = false;           // fused path: perturbed objects leave only head entries behind (k_svd16_l4 EPI 1), no q-form pass
     bool frame_full = false;     // lean mode: the current frame has been decomposed in full after all (a third triplet survived)
+    bool top1 = false;           // lean mode: perturbed objects by k_top1_l4 (dominant triplet + rigorous bound), exact on demand
+    double *dUp3 = nullptr;      // top1: perturbed window of object U2m (dUp keeps U2p's)
+    int *dLeanList = nullptr;    // top1: [0] count, [1..] patches whose bound survives at the current probe
+    double *dCrit = nullptr;     // top1: {critical lambda (exp weighting), largest bound (plain)} of the current frame
+    double crit_lambda = 0.0, crit_bound = 0.0;
+    double *hLean = nullptr;     // pinned: critical values / list count
     bool full_mode = false;      // stage_svd: write full records for the perturbed objects (fallback of the lean mode, probes)
     bool use_tile = false;       // atomics-free gather evaluation (tile_eval.cuh) on top of the fused path
     bool frame_fallback = false; // a third triplet survived at some probe of this frame: general k_eval3 path from there on
@@ -289,6 +295,9 @@ static void free_all(pguresvt_handle *h)
     if (h->hSum2)
         cudaFreeHost(h->hSum2);
     F(h->dSum2);
+    F(h->dUp3), F(h->dLeanList), F(h->dCrit);
+    if (h->hLean)
+        cudaFreeHost(h->hLean);
     F(h->dBinCnt), F(h->dBinStart), F(h->dScanSums), F(h->dEnt), F(h->dHead), F(h->dTilePart), F(h->dFth), F(h->dU0c);
     if (h->hOvf)
         cudaFreeHost(h->hOvf);
@@ -383,6 +392,7 @@ static int create_impl(pguresvt_handle *h)
     h->use_l4 = h->use_reg_svd && p.svd_kernel != 2; // 0 / 3: 4-lane kernel with tracked / recomputed pair norms
     h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
     h->lean = h->use_fused_eval && !(getenv("PGURESVT_LEAN") && atoi(getenv("PGURESVT_LEAN")) == 0);
+    h->top1 = h->lean && !(getenv("PGURESVT_TOP1") && atoi(getenv("PGURESVT_TOP1")) == 0);
     h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
     // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
     h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
@@ -492,6 +502,13 @@ static int create_impl(pguresvt_handle *h)
                 CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
         CU(cudaMalloc(&h->dHead, (size_t)TG_HEAD * h->P * sizeof(double)));
         CU(cudaMemset(h->dHead, 0, (size_t)TG_HEAD * h->P * sizeof(double)));
+        if (h->top1)
+        {
+            CU(cudaMalloc(&h->dUp3, wtot * sizeof(double)));
+            CU(cudaMalloc(&h->dLeanList, ((size_t)h->P + 1) * sizeof(int)));
+            CU(cudaMalloc(&h->dCrit, 2 * sizeof(double)));
+            CU(cudaMallocHost(&h->hLean, 4 * sizeof(double)));
+        }
         // the atomics-free gather evaluation (tile_eval.cuh) is exact and deterministic too, but on B200 its irregular gather costs
         // more instructions than the L2 atomic unit costs time: 1.0 ms against 0.55 ms per evaluation at 1024^2 (profiles/r02) —
         // opt-in with PGURESVT_TILE_EVAL=1
@@ -1215,9 +1232,22 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         if (obj != 0)
         { // U + eps*delta written out once (pgure.hpp:80-82); the SVD kernel then gathers plain doubles
             const size_t wtot = h->fsz * h->win;
-            k_perturb_window<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dU, pt, wtot, h->dUp);
+            double *dst = (h->top1 && obj == 3) ? h->dUp3 : h->dUp; // top1 keeps both perturbed windows for the exact fixes
+            if (!(h->top1 && h->full_mode)) // (already there when the frame falls back to full records)
+            {
+                k_perturb_window<<<std::min(cdiv(wtot, 256), h->sm_count * 16), 256, 0, h->st>>>(h->dU, pt, wtot, dst);
+                LAUNCHED(h);
+            }
+            usrc = dst;
+        }
+        if (h->top1 && obj != 0 && !h->full_mode)
+        { // dominant triplet + bound instead of the full decomposition (k_top1_l4)
+            k_top1_l4<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[0], h->dD2, pt.eps, h->d2Neg,
+                                                              h->d2Pos, h->dC4, h->dHead, part, 40, h->dSweeps);
             LAUNCHED(h);
-            usrc = h->dUp;
+            h->stats[1] += h->P;
+            CU(cudaGetLastError());
+            return PGS_OK;
         }
         // dynamic shared memory: V of object 0 for the warm start, re-used for the hand-over of z in the V rebuild (both variants)
         const int smem_svd = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
@@ -1225,10 +1255,10 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         CU(cudaFuncSetAttribute(obj == 0 ? cold : warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
         if (obj == 0)
             cold<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], nullptr,
-                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part);
+                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part, nullptr);
         else // perturbed objects start from the V of object 0 (computed first for this frame)
             warm<<<cdiv(nthreads, 128), 128, smem_svd, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[obj], h->dFac[0],
-                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part);
+                                                                max_sweeps, tol2, big2, h->dSweeps, h->dC4, h->dHead, part, nullptr);
     }
     else if (h->use_reg_svd)
     {
@@ -1456,6 +1486,63 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
     return launch_recon_generic(h, h->dFac[obj], h->dIds, h->P, lambda, only_k, h->dAcc[obj]);
 }
 
+// top1 mode, per frame: the critical lambda of the bounds the perturbed objects were given (k_lean_crit)
+static int lean_crit(pguresvt_handle *h)
+{
+    h->hLean[0] = INFINITY, h->hLean[1] = 0.0;
+    CU(cudaMemcpyAsync(h->dCrit, h->hLean, 2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    k_lean_crit<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, h->dCrit);
+    LAUNCHED(h);
+    CU(cudaMemcpyAsync(h->hLean, h->dCrit, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->crit_lambda = h->hLean[0];
+    h->crit_bound = h->hLean[1];
+    return PGS_OK;
+}
+
+// top1 mode, before an evaluation at `lambda`: every patch whose bound would survive the threshold there is decomposed
+// exactly (both perturbed objects, warm-started Jacobi over the list), so the evaluation sees exact head entries wherever
+// they matter.  Probes on the safe side of the frame's critical lambda skip even the check.
+static int lean_fix(pguresvt_handle *h, double lambda)
+{
+    if (!h->top1 || h->frame_full)
+        return PGS_OK;
+    const bool maybe = h->p.exp_weighting ? !(lambda <= h->crit_lambda) : !(lambda >= h->crit_bound);
+    if (!maybe)
+        return PGS_OK;
+    CU(cudaMemsetAsync(h->dLeanList, 0, sizeof(int), h->st));
+    k_lean_check<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, h->p.exp_weighting, h->dLeanList);
+    LAUNCHED(h);
+    int *hcnt = reinterpret_cast<int *>(h->hLean + 2);
+    CU(cudaMemcpyAsync(hcnt, h->dLeanList, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const int n = *hcnt;
+    h->stats[22] += 1;
+    // every patch still carrying a bound is safe at this lambda once the listed ones are exact: the safe side grows
+    if (h->p.exp_weighting)
+        h->crit_lambda = std::max(h->crit_lambda, lambda);
+    else
+        h->crit_bound = std::min(h->crit_bound, lambda);
+    if (n == 0)
+        return PGS_OK;
+    h->stats[20] += n;
+    const int variant = h->p.svd_kernel == 3 ? 0 : h->p.svd_kernel == 4 ? 1 : 2;
+    auto warm = variant == 2 ? k_svd16_l4<1, 2, 1> : variant == 1 ? k_svd16_l4<1, 1, 1> : k_svd16_l4<1, 0, 1>;
+    const int smem_svd = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
+    CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
+    const double big = 1e-6, tol = 1e-15;
+    for (int obj = 2; obj <= 3; obj++)
+    {
+        warm<<<cdiv((long long)n * 4, 128), 128, smem_svd, h->st>>>(obj == 2 ? h->dUp : h->dUp3, h->dPos, h->dIds, n, h->vecSize, h->N, nullptr,
+                                                                    h->dFac[0], 30, tol * tol, big * big, nullptr, h->dC4, h->dHead, obj - 1,
+                                                                    h->dLeanList + 1);
+        LAUNCHED(h);
+        h->stats[23] += n;
+    }
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+
 // Lean mode, exact fallback: a third singular triplet of some object survived at the probed lambda (or a probe asks for the
 // factors of a perturbed object).  The perturbed objects are decomposed again with full records, all q-forms are prepared
 // and the rest of the frame runs through the general evaluation.
@@ -1491,6 +1578,11 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     { // afterwards every evaluation's voxel pass leaves the accumulator cleared
         CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
         h->acc0_clean = true;
+    }
+    {
+        int rcf = lean_fix(h, lambda);
+        if (rcf)
+            return rcf;
     }
     for (int attempt = 0; attempt < 2; attempt++)
     {
@@ -1579,6 +1671,11 @@ static int objective_tile(pguresvt_handle *h, double lambda, double alpha, doubl
 {
     if (h->frame_fallback)
         return objective_fused(h, lambda, alpha, mu, sigma, value, terms);
+    {
+        int rcf = lean_fix(h, lambda);
+        if (rcf)
+            return rcf;
+    }
     const int nw = cdiv(h->P, 32), ntile = h->tile_r * h->tile_c * (int)h->win;
     k_thresh<<<cdiv(h->P, 256), 256, 0, h->st>>>(h->dHead, h->P, lambda, h->p.exp_weighting, h->dFth, h->dPartialE, h->dKpart, h->dNeedQ);
     LAUNCHED(h);
@@ -1661,7 +1758,9 @@ static int sum_u_launch(pguresvt_handle *h)
     const size_t wtot = h->fsz * h->win;
     CU(cudaEventRecord(h->evU, h->st));
     CU(cudaStreamWaitEvent(h->sum_st, h->evU, 0));
-    k_accu_seq<<<2, AS_THREADS, 0, h->sum_st>>>(h->dU, wtot, h->dSum2);
+    const int smem_as = AS_THREADS * (AS_E + 1) * (int)sizeof(double);
+    CU(cudaFuncSetAttribute(k_accu_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_as));
+    k_accu_seq<<<2, AS_THREADS, smem_as, h->sum_st>>>(h->dU, wtot, h->dSum2);
     LAUNCHED(h);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->hSum2, h->dSum2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->sum_st));
@@ -1801,8 +1900,12 @@ static int prepare_frame(pguresvt_handle *h, uint32_t t)
     {
         StageTimer tm(h, 17);
         h->frame_full = false;
-        if (h->lean) // the SVD kernels left the head entries (S, leading q-forms) behind: nothing to prepare
+        if (h->lean)
+        { // the SVD kernels left the head entries (S, leading q-forms) behind: nothing to prepare
             CU(cudaMemsetAsync(h->dNeedQ, 0, sizeof(double), h->st));
+            if (h->top1 && (rc = lean_crit(h)))
+                return rc;
+        }
         else if ((rc = launch_qform(h, QFORM_LAZY_K))) // q = u^T C4 v of the leading triplets (the rest lazily, see objective_fused)
             return rc;
         if (h->use_tile && (rc = tile_prepare(h)))

@@ -522,8 +522,8 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(const double *__restrict__
 // preconditions fail (binade crossing, addend not smaller than the accumulator, zero accumulator) the offending thread's
 // few elements are added with real FP64 adds and the scan resumes behind it.
 // ------------------------------------------------------------------------------------------------------------------------
-#define AS_THREADS 512
-#define AS_E 8 /* elements per thread and chunk */
+#define AS_THREADS 256
+#define AS_E 32 /* elements per thread and chunk (the block scan is amortised over them: 8 per thread took 15 ms per window) */
 struct AsFn
 {
     unsigned long long c1, c2;
@@ -572,29 +572,47 @@ __global__ void __launch_bounds__(AS_THREADS) k_accu_seq(const double *__restric
     __shared__ AsFn wfn[AS_THREADS / 32];
     __shared__ double s_acc;
     __shared__ int s_stop;
-    __shared__ double stage[AS_THREADS * AS_E + AS_THREADS]; // the chunk, element j at j + j / 8 (conflict-free per-thread runs)
+    extern __shared__ double stage[]; // the chunk: AS_THREADS * (AS_E + 1) doubles, element j at j + j / AS_E (conflict-free runs)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double acc = 0.0;
     for (size_t base = 0; base < nel && acc == acc; base += (size_t)AS_THREADS * AS_E)
     {
-        // coalesced 16-byte loads of (even, odd) pairs, this accumulator's half staged in shared memory
-#pragma unroll
-        for (int r = 0; r < AS_E; r++)
+        // coalesced 16-byte loads of (even, odd) pairs, this accumulator's half staged in shared memory.  All loads of a full
+        // chunk are issued before the first one is consumed (one DRAM latency per chunk, not one per element: the first version
+        // selected and stored right behind every load and took 21 us per chunk)
+        if (2 * (base + (size_t)AS_THREADS * AS_E) <= n)
         {
-            const int jl = r * AS_THREADS + threadIdx.x;
-            const size_t j = base + jl;
-            double v = 0.0;
-            if (j < nel)
+            double2 pr[AS_E];
+#pragma unroll
+            for (int r = 0; r < AS_E; r++)
+                pr[r] = __ldg(reinterpret_cast<const double2 *>(u) + base + r * AS_THREADS + threadIdx.x);
+#pragma unroll
+            for (int r = 0; r < AS_E; r++)
             {
-                if (2 * j + 1 < n)
-                {
-                    const double2 pr = reinterpret_cast<const double2 *>(u)[j];
-                    v = par ? pr.y : pr.x;
-                }
-                else
-                    v = u[2 * j + par];
+                const int jl = r * AS_THREADS + threadIdx.x;
+                stage[jl + jl / AS_E] = par ? pr[r].y : pr[r].x;
             }
-            stage[jl + (jl >> 3)] = v;
+        }
+        else
+        {
+#pragma unroll 1
+            for (int r = 0; r < AS_E; r++)
+            {
+                const int jl = r * AS_THREADS + threadIdx.x;
+                const size_t j = base + jl;
+                double v = 0.0;
+                if (j < nel)
+                {
+                    if (2 * j + 1 < n)
+                    {
+                        const double2 pr = reinterpret_cast<const double2 *>(u)[j];
+                        v = par ? pr.y : pr.x;
+                    }
+                    else
+                        v = u[2 * j + par];
+                }
+                stage[jl + jl / AS_E] = v;
+            }
         }
         __syncthreads();
         // this thread's AS_E consecutive elements of the chunk
@@ -615,34 +633,52 @@ __global__ void __launch_bounds__(AS_THREADS) k_accu_seq(const double *__restric
             bool bad = false;
             if ((int)threadIdx.x >= seg)
             {
+                // the elements' increments are independent of each other; only an exact tie (rare: the dropped bits equal
+                // half an ulp exactly) makes the composition order-dependent, so the common case is a plain integer sum
+                unsigned long long incs[AS_E];
+                unsigned tiemask = 0u;
 #pragma unroll
                 for (int k = 0; k < AS_E; k++)
                 {
                     const long long b = __double_as_longlong(a[k]);
-                    if (b == 0)
-                        continue; // +0.0: identity
                     const int eb = (int)((b >> 52) & 0x7ff);
                     const int sh = ebias - eb;
+                    incs[k] = 0ull;
+                    if (b == 0)
+                        continue; // +0.0: identity
                     if (!acc_ok || b < 0 || eb == 0 || sh < 1)
                     { // zero / non-finite accumulator, negative, subnormal or not-smaller addend: real adds for this thread
                         bad = true;
                         continue;
                     }
-                    unsigned long long q = 0ull;
-                    int up = 0, tie = 0;
                     if (sh < 64)
                     {
                         const unsigned long long m = ((unsigned long long)b & ((1ull << 52) - 1)) | (1ull << 52);
-                        q = m >> sh;
                         const unsigned long long rem = m & ((1ull << sh) - 1), half = 1ull << (sh - 1);
-                        up = rem > half;
-                        tie = rem == half;
+                        incs[k] = (m >> sh) + (rem > half ? 1ull : 0ull);
+                        if (rem == half)
+                            tiemask |= 1u << k;
                     }
-                    AsFn g;
-                    g.tie = tie;
-                    g.c1 = q + (unsigned long long)up;
-                    g.c2 = 0ull;
-                    f = as_compose(f, g);
+                }
+                if (tiemask == 0u)
+                {
+                    unsigned long long t = 0ull;
+#pragma unroll
+                    for (int k = 0; k < AS_E; k++)
+                        t += incs[k]; // (each below 2^52: no overflow)
+                    f.c1 = t > AS_SAT ? AS_SAT : t;
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < AS_E; k++)
+                    {
+                        AsFn g;
+                        g.tie = (tiemask >> k) & 1u;
+                        g.c1 = incs[k];
+                        g.c2 = 0ull;
+                        f = as_compose(f, g);
+                    }
                 }
             }
             // inclusive scan of the functions over the block (identity for finished threads)

@@ -48,7 +48,7 @@ DTYPES = {np.dtype("uint8"): 0, np.dtype("uint16"): 1, np.dtype("float32"): 2, n
 NSTATS = 24
 STAT_NAMES = ["launches", "svds", "evals", "ms_median", "ms_arps", "ms_svd", "ms_search", "ms_final", "ms_noise",
               "ms_total", "svd_sweeps", "factor_bytes", "sweeps_obj0", "sweeps_warm", "arps_pairs_computed", "arps_pairs_reused", "eval_triplets", "ms_search_prep", "eval_redone", "evals_memoized",
-              "overflow_patches", "rank_cache"]
+              "overflow_patches", "rank_cache", "lean_checks", "lean_exact_svds"]
 
 
 def lib_path():
