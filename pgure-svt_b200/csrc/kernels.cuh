@@ -1723,9 +1723,17 @@ __global__ void __launch_bounds__(128, 2)
 // evaluation, so every probe is answered exactly (soft_f is monotone in s: a bound that does not survive proves that no
 // singular value below it does).  4 lanes per matrix like k_svd16_l4.
 // ------------------------------------------------------------------------------------------------------
+// MODE 0: perturbed object, object U decomposed exactly (bound = min(Weyl, Gram), start and shift from U's record);
+// MODE 1: perturbed object, object U itself in top-1 form (bound from the Gram matrix; start from U's v_1);
+// MODE 2: object U: cold start from the constant vector; leaves a minimal record (u_1, v_1, S = (sigma_1, 0, ..), slot 15 =
+//         sigma_1) for the consumers of the leading triplet, plus the head entries.
+// Gram bound: with G = A^T A - sigma_1^2 v_1 v_1^T (eigenvalues sigma_2^2 .. sigma_15^2),  sigma_2^4 <= sum_k>=2 sigma_k^4 =
+// ||G||_F^2, i.e. sigma_2 <= ||G||_F^(1/2) — 1.2 x sigma_2 on noise-dominated patches (the Frobenius norm of the residual
+// itself is 1.9 x: too loose, the bound would "survive" on a sixth of the patches at the lambdas the search settles on).
+template <int MODE>
 __global__ void __launch_bounds__(128, 2)
     k_top1_l4(const double *__restrict__ u, const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N,
-              const double *__restrict__ fac0, const int8_t *__restrict__ d2neg, double eps2, double dNeg, double dPos,
+              double *__restrict__ fac0, const int8_t *__restrict__ d2neg, double eps2, double dNeg, double dPos,
               const double *__restrict__ c4, double *__restrict__ head, int part, int max_iters, int *__restrict__ iters_out)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1738,6 +1746,7 @@ __global__ void __launch_bounds__(128, 2)
     const size_t fsz = (size_t)N * N;
     double a[4][SVD16_N];
     int nneg = 0;
+    double fro2 = 0.0;
 #pragma unroll
     for (int k = 0; k < SVD16_N; k++)
     {
@@ -1747,28 +1756,33 @@ __global__ void __launch_bounds__(128, 2)
         for (int r = 0; r < 4; r++)
         {
             a[r][k] = __ldg(u + vox + r);
-            nneg += d2neg[vox + r] ? 1 : 0;
+            fro2 = fma(a[r][k], a[r][k], fro2);
+            if (MODE == 0)
+                nneg += d2neg[vox + r] ? 1 : 0;
         }
     }
-    const double *R0 = fac0 + (size_t)SVD16_REC * pidx;
+    fro2 += __shfl_xor_sync(0xffffffffu, fro2, 1);
+    fro2 += __shfl_xor_sync(0xffffffffu, fro2, 2);
+    double *R0 = fac0 + (size_t)SVD16_REC * pidx;
     double x[SVD16_N];
     double xn2 = 0.0;
 #pragma unroll
     for (int j = 0; j < SVD16_N; j++)
     {
-        x[j] = R0[SVD16_M * SVD16_N + j]; // v_1 of object U
+        x[j] = (MODE == 2) ? 0.0 : R0[SVD16_M * SVD16_N + j]; // v_1 of object U
         xn2 = fma(x[j], x[j], xn2);
     }
     if (!(xn2 > 0.5))
-    { // rank-deficient object U (zero patch): start from the constant vector
+    { // object U itself, or a rank-deficient object U (zero patch): start from the constant vector
 #pragma unroll
         for (int j = 0; j < SVD16_N; j++)
             x[j] = 0.2581988897471611; // 1 / sqrt(15)
     }
-    // shifted iteration x <- (A^T A - mu) x with mu at the centre of object U's unwanted spectrum [sigma_15^2, sigma_2^2]:
-    // contraction (sigma_2^2 - sigma_15^2) / (2 sigma_1^2 - sigma_2^2 - sigma_15^2) per step instead of (sigma_2 / sigma_1)^2
-    // (the shift only steers convergence; sigma_1 and u_1 come from the final A v_1)
+    // shifted iteration x <- (A^T A - mu) x with mu near the centre of the unwanted spectrum [sigma_15^2, sigma_2^2]: contraction
+    // (sigma_2^2 - sigma_15^2) / (2 sigma_1^2 - sigma_2^2 - sigma_15^2) per step instead of (sigma_2 / sigma_1)^2.  The shift only
+    // steers convergence; sigma_1 and u_1 come from the final A v_1.
     double mu_shift = 0.0;
+    if (MODE == 0)
     {
         const double *S0 = R0 + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
         mu_shift = 0.5 * (S0[1] * S0[1] + S0[14] * S0[14]);
@@ -1781,6 +1795,7 @@ __global__ void __launch_bounds__(128, 2)
 #pragma unroll 1
     for (; it < max_iters; it++)
     {
+        double y2 = 0.0;
 #pragma unroll
         for (int r = 0; r < 4; r++)
         {
@@ -1793,6 +1808,15 @@ __global__ void __launch_bounds__(128, 2)
                 s2 = fma(a[r][j + 2], x[j + 2], s2);
             }
             y[r] = (s0 + s1) + s2;
+            y2 = fma(y[r], y[r], y2);
+        }
+        if (MODE != 0 && it == 0)
+        { // no spectrum of object U to take the shift from: mean of the unwanted eigenvalues from ||A||_F^2 - ||A x0||^2
+            y2 += __shfl_xor_sync(0xffffffffu, y2, 1);
+            y2 += __shfl_xor_sync(0xffffffffu, y2, 2);
+            mu_shift = fmax(fro2 - y2, 0.0) * (1.0 / 14.0);
+            if (!(mu_shift < 0.25 * y2))
+                mu_shift = 0.0;
         }
         double z[SVD16_N], n2 = 0.0;
 #pragma unroll
@@ -1845,6 +1869,37 @@ __global__ void __launch_bounds__(128, 2)
     s2sum += __shfl_xor_sync(0xffffffffu, s2sum, 2);
     const double sig1 = sqrt(s2sum);
     const double isig = sig1 > 0.0 ? 1.0 / sig1 : 0.0;
+    // ||G||_F^2 = ||A^T A||_F^2 - sigma_1^4 (A^T A v_1 = sigma_1^2 v_1): the 120 entries of the upper triangle of A^T A in groups
+    // of 16 partial inner products, each group summed over the four lanes by one transposing reduction (tr4_16); off-diagonal
+    // entries carry a factor sqrt(2) so that their squares count twice.  The subtraction cancels (sigma_2 / sigma_1)^4 of the
+    // leading digits: 1e-13 sigma_1^4 is added back as the rounding allowance that keeps the bound rigorous.
+    double g2 = 0.0;
+    {
+        double part16[16];
+        int cnt16 = 0;
+#pragma unroll
+        for (int i = 0; i < SVD16_N; i++)
+#pragma unroll
+            for (int j = i; j < SVD16_N; j++)
+            {
+                const double pij = fma(a[0][i], a[0][j], fma(a[1][i], a[1][j], fma(a[2][i], a[2][j], a[3][i] * a[3][j])));
+                part16[cnt16] = (i == j) ? pij : 1.4142135623730951 * pij;
+                cnt16++;
+                if (cnt16 == 16 || (i == SVD16_N - 1 && j == SVD16_N - 1))
+                {
+#pragma unroll
+                    for (int q = cnt16; q < 16; q++)
+                        part16[q] = 0.0;
+                    double tot[4];
+                    tr4_16(part16, sub, tot);
+                    g2 = fma(tot[0], tot[0], fma(tot[1], tot[1], fma(tot[2], tot[2], fma(tot[3], tot[3], g2))));
+                    cnt16 = 0;
+                }
+            }
+    }
+    g2 += __shfl_xor_sync(0xffffffffu, g2, 1);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, 2);
+    g2 = fmax(g2 * (1.0 + 1e-13) - s2sum * s2sum, 0.0) + 1e-13 * s2sum * s2sum;
     // q-form u_1^T C4 v_1 (C4 gathered along the trajectory, the same voxels as the matrix)
     double qf = 0.0;
     {
@@ -1864,15 +1919,40 @@ __global__ void __launch_bounds__(128, 2)
     }
     qf += __shfl_xor_sync(0xffffffffu, qf, 1);
     qf += __shfl_xor_sync(0xffffffffu, qf, 2);
-    nneg += __shfl_xor_sync(0xffffffffu, nneg, 1);
-    nneg += __shfl_xor_sync(0xffffffffu, nneg, 2);
+    if (MODE == 0)
+    {
+        nneg += __shfl_xor_sync(0xffffffffu, nneg, 1);
+        nneg += __shfl_xor_sync(0xffffffffu, nneg, 2);
+    }
+    double bound = sqrt(sqrt(g2)) * (1.0 + 1e-9);
+    if (MODE == 0)
+    { // Weyl: sigma_k(A + E) <= sigma_2(A) + ||E||_F for k >= 2, with object U's exact sigma_2
+        const double e2 = (double)nneg * dNeg * dNeg + (double)(SVD16_M * SVD16_N - nneg) * dPos * dPos;
+        const double s2u = R0[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 1];
+        bound = fmin(bound, (s2u + eps2 * sqrt(e2)) * (1.0 + 1e-12));
+    }
+    if (!conv)
+        bound = INFINITY; // not converged within max_iters (dominant pair not separated): exact decomposition on first use
+    if (MODE == 2 && valid)
+    { // minimal record of object U: u_1, v_1, S = (sigma_1, 0, ...), slot 15 = sigma_max
+        double2 *ud = reinterpret_cast<double2 *>(R0 + 4 * sub);
+        ud[0] = make_double2(y[0] * isig, y[1] * isig);
+        ud[1] = make_double2(y[2] * isig, y[3] * isig);
+        double *Vd = R0 + SVD16_M * SVD16_N, *Sd = R0 + SVD16_M * SVD16_N + SVD16_LDV * SVD16_N;
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+        {
+            const int j = 4 * sub + e;
+            double xv = 0.0;
+#pragma unroll
+            for (int q = 0; q < SVD16_N; q++)
+                xv = (q == j) ? x[q] : xv;
+            Vd[j] = (j < SVD16_N) ? xv : 0.0;
+            Sd[j] = (j == 0 || j == 15) ? sig1 : 0.0;
+        }
+    }
     if (valid && sub == 0)
     {
-        const double e2 = (double)nneg * dNeg * dNeg + (double)(SVD16_M * SVD16_N - nneg) * dPos * dPos;
-        const double s2u = R0[SVD16_M * SVD16_N + SVD16_LDV * SVD16_N + 1]; // sigma_2 of object U
-        double bound = (s2u + eps2 * sqrt(e2)) * (1.0 + 1e-12);
-        if (!conv)
-            bound = INFINITY; // not converged within max_iters (dominant pair not separated): exact decomposition on first use
         double *hd = head + (size_t)16 * pidx;
         hd[3 * part] = sig1;
         hd[3 * part + 1] = bound;
@@ -1900,7 +1980,7 @@ __global__ void k_lean_crit(const double *__restrict__ head, int P, double *__re
     {
         const double *hd = head + (size_t)16 * pidx;
 #pragma unroll
-        for (int part = 1; part <= 2; part++)
+        for (int part = 0; part <= 2; part++)
             if (hd[3 * part + 2] < 0.0)
             {
                 const double s1 = hd[3 * part], B = hd[3 * part + 1];
@@ -1931,7 +2011,7 @@ __global__ void k_lean_check(const double *__restrict__ head, int P, double lamb
     const double *hd = head + (size_t)16 * pidx;
     bool off = false;
 #pragma unroll
-    for (int part = 1; part <= 2; part++)
+    for (int part = 0; part <= 2; part++)
         if (hd[3 * part + 2] < 0.0)
         {
             const double s1 = hd[3 * part], B = hd[3 * part + 1];

@@ -80,6 +80,7 @@ struct pguresvt_handle
     bool use_fused_eval = false;
     bool lean = false;           // fused path: perturbed objects leave only head entries behind (k_svd16_l4 EPI 1), no q-form pass
     bool frame_full = false;     // lean mode: the current frame has been decomposed in full after all (a third triplet survived)
+    bool top1_all = false;       // top1 for object U as well (bound from the Gram matrix): no Jacobi launch in the common case
     bool top1 = false;           // lean mode: perturbed objects by k_top1_l4 (dominant triplet + rigorous bound), exact on demand
     double *dUp3 = nullptr;      // top1: perturbed window of object U2m (dUp keeps U2p's)
     int *dLeanList = nullptr;    // top1: [0] count, [1..] patches whose bound survives at the current probe
@@ -393,6 +394,7 @@ static int create_impl(pguresvt_handle *h)
     h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
     h->lean = h->use_fused_eval && !(getenv("PGURESVT_LEAN") && atoi(getenv("PGURESVT_LEAN")) == 0);
     h->top1 = h->lean && !(getenv("PGURESVT_TOP1") && atoi(getenv("PGURESVT_TOP1")) == 0);
+    h->top1_all = h->top1 && !(getenv("PGURESVT_TOP1_ALL") && atoi(getenv("PGURESVT_TOP1_ALL")) == 0);
     h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
     // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
     h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
@@ -1240,10 +1242,11 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
             }
             usrc = dst;
         }
-        if (h->top1 && obj != 0 && !h->full_mode)
+        if (h->top1 && !h->full_mode && (obj != 0 || h->top1_all))
         { // dominant triplet + bound instead of the full decomposition (k_top1_l4)
-            k_top1_l4<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[0], h->dD2, pt.eps, h->d2Neg,
-                                                              h->d2Pos, h->dC4, h->dHead, part, 40, h->dSweeps);
+            auto ktop = obj == 0 ? k_top1_l4<2> : h->top1_all ? k_top1_l4<1> : k_top1_l4<0>;
+            ktop<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[0], h->dD2, pt.eps, h->d2Neg,
+                                                         h->d2Pos, h->dC4, h->dHead, part, 40, h->dSweeps);
             LAUNCHED(h);
             h->stats[1] += h->P;
             CU(cudaGetLastError());
@@ -1531,6 +1534,15 @@ static int lean_fix(pguresvt_handle *h, double lambda)
     const int smem_svd = 32 * SVD16_V0_STRIDE * (int)sizeof(double);
     CU(cudaFuncSetAttribute(warm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
     const double big = 1e-6, tol = 1e-15;
+    if (h->top1_all)
+    { // object U first (cold, full record + head entries): the perturbed objects start from its V
+        auto cold = variant == 2 ? k_svd16_l4<0, 2, 2> : variant == 1 ? k_svd16_l4<0, 1, 2> : k_svd16_l4<0, 0, 2>;
+        CU(cudaFuncSetAttribute(cold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_svd));
+        cold<<<cdiv((long long)n * 4, 128), 128, smem_svd, h->st>>>(h->dU, h->dPos, h->dIds, n, h->vecSize, h->N, h->dFac[0], nullptr, 30, tol * tol,
+                                                                    big * big, nullptr, h->dC4, h->dHead, 0, h->dLeanList + 1);
+        LAUNCHED(h);
+        h->stats[23] += n;
+    }
     for (int obj = 2; obj <= 3; obj++)
     {
         warm<<<cdiv((long long)n * 4, 128), 128, smem_svd, h->st>>>(obj == 2 ? h->dUp : h->dUp3, h->dPos, h->dIds, n, h->vecSize, h->N, nullptr,
@@ -1552,7 +1564,7 @@ static int ensure_full(pguresvt_handle *h)
         return PGS_OK;
     int rc;
     h->full_mode = true;
-    for (int obj = 2; obj <= 3; obj++)
+    for (int obj = h->top1_all ? 0 : 2; obj <= 3; obj += (obj == 0 ? 2 : 1))
         if ((rc = stage_svd(h, obj)))
         {
             h->full_mode = false;
@@ -2459,7 +2471,7 @@ extern "C" int pguresvt_probe_arps(pguresvt_handle *h, uint32_t t, int32_t *patc
 extern "C" int pguresvt_probe_singular_values(pguresvt_handle *h, uint32_t t, int obj, double *S, int64_t *n_patches)
 {
     CHECK_T(h, t);
-    const bool lean_obj = h->lean && (obj == 2 || obj == 3);
+    const bool lean_obj = (h->lean && (obj == 2 || obj == 3)) || (h->top1_all && obj == 0);
     if (obj < 0 || obj > 3 || !(h->dFac[obj] || h->dSc[obj] || lean_obj))
         return fail(PGS_ERR_ARG, "SVT object %d not present in this configuration", obj);
     int rc = prepare_frame(h, t);
@@ -2508,6 +2520,8 @@ extern "C" int pguresvt_probe_reconstruct(pguresvt_handle *h, uint32_t t, double
     if (!h->p.optimize_pgure)
         if ((rc = stage_count(h, -1)))
             return rc;
+    if (h->top1_all && (rc = ensure_full(h))) // the whole-window reconstruction reads complete records of object U
+        return rc;
     if ((rc = launch_recon(h, 0, lambda, -1)))
         return rc;
     if (!h->dV)
