@@ -6,5 +6,13 @@ library raises — there is no CPU fallback.
 """
 from .svt import SVT, mixed_noise_model
 
-__all__ = ["mixed_noise_model", "SVT"]
-__version__ = "0.6.4+b200.1"
+
+def release_cached():
+    """Free the per-device handles (device buffers, page-locked staging) the one-shot entry points keep between calls."""
+    from ._pguresvt import release_cached as _rc
+
+    _rc()
+
+
+__all__ = ["mixed_noise_model", "SVT", "release_cached"]
+__version__ = "0.6.4+b200.2"

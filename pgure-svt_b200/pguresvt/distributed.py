@@ -56,7 +56,14 @@ def denoise_sharded(X, compute_block=None, group=None, **kw):
         Yall, eall = Yb, eb
     else:
         use_cuda = dist.get_backend(group) == "nccl"
-        dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+        if use_cuda:
+            # gather on the SAME device the C ABI computes on (make_params: PGURESVT_DEVICE / LOCAL_RANK), not on whatever
+            # torch's current device happens to be: every rank on cuda:0 is an NCCL duplicate-GPU error
+            from ._pguresvt import make_params
+
+            dev = torch.device("cuda", int(kw.get("device", make_params().device)))
+        else:
+            dev = torch.device("cpu")
         ty, te = torch.from_numpy(Yb).to(dev), torch.from_numpy(eb).to(dev)
         gy = torch.empty((world * per, nc, nr), dtype=ty.dtype, device=dev)
         ge = torch.empty((world * per, 4), dtype=te.dtype, device=dev)

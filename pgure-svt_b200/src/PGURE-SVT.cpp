@@ -86,6 +86,12 @@ int main(int argc, char **argv)
         return -1;
     }
     const uint32_t W = tif.page(0).width, H = tif.page(0).height;
+    for (uint32_t d = 0; d < tif.n_pages(); d++) // every page must have the geometry of the first (the cube is sized from page 0)
+        if (tif.page(d).width != W || tif.page(d).height != H)
+        {
+            pguresvt::Print(std::cerr, "**ERROR**\nTIFF page ", d + 1, " is ", tif.page(d).width, "x", tif.page(d).height, ", page 1 is ", W, "x", H, "\n");
+            return -1;
+        }
     const uint16_t depth = tif.page(0).bits;
     if (W != H)
     {

@@ -108,6 +108,8 @@ private:
         const size_t sz = (type == 3) ? 2 : (type == 4) ? 4 : (type == 1) ? 1 : 0;
         if (!sz)
             return fail("unsupported tag type");
+        if (count == 0 || count > (1u << 26)) // (the callers index out[0]; a hostile count must not size a buffer)
+            return fail("tag with an empty or absurd value count");
         std::vector<unsigned char> buf((size_t)count * sz);
         if (buf.size() <= 4)
             std::memcpy(buf.data(), field, buf.size());

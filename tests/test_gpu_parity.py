@@ -213,7 +213,7 @@ def test_pgure_lambda_golden(golden):
     s = SVT(noise_alpha=alpha, noise_mu=mu, noise_sigma=sigma, random_seed=1).denoise(X)
     est = golden["est_pgure"]
     assert np.abs(s.lambda1s_ - est[:, 0]).max() / np.abs(est[:, 0]).max() < LAM_TOL
-    assert per_frame_rel_err(s.Y_, golden["Y_pgure"]) < 1e-4  # lambda differs within tolerance → pixels follow
+    assert per_frame_rel_err(s.Y_, golden["Y_pgure"]) < PIX_TOL
     assert np.array_equal(s.noise_alphas_, est[:, 1]) and np.array_equal(s.noise_sigmas_, est[:, 3])
 
 
@@ -228,11 +228,12 @@ def test_reference_test_cases_on_gpu(ref_test_cube):
     s = SVT(noise_alpha=0.0109, noise_mu=100.0, noise_sigma=100.0, random_seed=101).denoise(Y)
     ref, est = orc.pguresvt(Y, lambda1=-1.0, noise_alpha=0.0109, noise_mu=100.0, noise_sigma=100.0, random_seed=101)
     assert nsed(X, s.Y_) < 0.3
-    # raw-unit noise parameters (mu = sigma = 100 on max-normalised data, as the reference's test passes them)
-    # put a -1e4 offset on the risk, so the optimiser's comparisons sit at the FP64 noise floor and a frame may
-    # take a different but equally valid path: require agreement on the large majority of frames
+    # raw-unit noise parameters (mu = sigma = 100 on max-normalised data, as the reference's test passes them) put a -1e4
+    # offset on the risk.  Round 1 accepted 80 % of the frames here; the divergence came from the START POINT of the search
+    # (a tree-ordered sum of u instead of Armadillo's sequential accu): with the exact sum every frame follows the oracle.
     rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
-    assert (rel < LAM_TOL).mean() >= 0.8, rel
+    assert rel.max() < LAM_TOL, rel
+    assert per_frame_rel_err(s.Y_, ref) < PIX_TOL
 
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32, np.float64])
@@ -417,7 +418,7 @@ def test_default_api_estimates_noise(golden):
     assert np.allclose(s.noise_sigmas_, est[:, 3], rtol=1e-6)
     rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
     assert rel.max() < LAM_TOL, rel
-    assert per_frame_rel_err(s.Y_, ref) < 1e-4
+    assert per_frame_rel_err(s.Y_, ref) < PIX_TOL
 
 
 def test_reference_default_test_on_gpu(ref_test_cube):
@@ -513,7 +514,7 @@ def test_edge_case_pgure_small_windows():
     ref, est = orc.pguresvt(X, **args)
     rel = np.abs(s.lambda1s_ - est[:, 0]) / np.abs(est[:, 0])
     assert rel.max() < LAM_TOL, rel
-    assert per_frame_rel_err(s.Y_, ref) < 1e-4
+    assert per_frame_rel_err(s.Y_, ref) < PIX_TOL
 
 
 @pytest.mark.parametrize("rank_cache", [0, 1, -1])
@@ -533,7 +534,7 @@ def test_config5_shape_pgure_small(rank_cache):
     h.close()
     ref, est = orc.pguresvt(X, frame_begin=t, frame_end=t + 1, **args)
     assert abs(eh[t, 0] - est[t, 0]) / abs(est[t, 0]) < LAM_TOL
-    assert np.abs(Yh[:, :, t] - ref[:, :, t]).max() / np.abs(ref[:, :, t]).max() < 1e-4
+    assert np.abs(Yh[:, :, t] - ref[:, :, t]).max() / np.abs(ref[:, :, t]).max() < PIX_TOL
     if rank_cache == 1:
         assert st["overflow_patches"] > 0 and st["rank_cache"] == 1
     if rank_cache == -1:
@@ -555,19 +556,10 @@ def test_warp_svd_other_shapes_pgure(kw):
     Yh, eh = h.download()
     ref, est = orc.pguresvt(X, frame_begin=t, frame_end=t + 2, **args)
     for f in (t, t + 1):
-        lam_rel = abs(eh[f, 0] - est[f, 0]) / abs(est[f, 0])
-        pix_tol = 1e-4
-        if lam_rel >= LAM_TOL:
-            # Plain thresholding of 64x31 patches gives an objective that is flat to ~3e-8 relative over +-0.5 % in lambda
-            # (tools/diag_plain2.py): the search's own ftol_rel is 1e-7, so its end point inside that basin hinges on
-            # near-ties between probes.  EVERY device path (warp / shared-memory SVD, compact / full cache) ends at the
-            # same lambda, the oracle at another point of the basin; with motion estimation off they coincide to 1e-14.
-            # Accept iff both end points are equivalent for the search: same objective value within a few ftol_rel (the
-            # search returns its LAST probe, not its best one — SURVEY Q2 — so the end point sits anywhere in the final simplex).
-            assert not kw.get("exponential_weighting", True)
-            v, _ = h.probe_pgure(f, 0.1, 0.05, 0.05, np.array([eh[f, 0], est[f, 0]]))
-            assert abs(v[0] - v[1]) <= 1e-6 * abs(v[1]) and lam_rel < 1e-2
-            pix_tol = 1e-3
+        # (round 1 accepted the plain-thresholding case on the objective value only: its search ended elsewhere in a flat
+        #  basin.  The cause was the start point of the search — see k_accu_seq — and is gone: lambda agrees on every case.)
+        assert abs(eh[f, 0] - est[f, 0]) / abs(est[f, 0]) < LAM_TOL
+        pix_tol = PIX_TOL
         assert np.abs(Yh[:, :, f] - ref[:, :, f]).max() / np.abs(ref[:, :, f]).max() < pix_tol
     h.close()
 
@@ -691,7 +683,7 @@ def test_full_size_properties_1024_pgure():
     assert out[0][3]["svds"] == 3 * 1021 * 1021
     assert np.abs(out[0][0] - out[1][0]).max() <= 1e-9 * np.abs(out[1][0]).max()
     assert abs(out[0][2] - out[1][2]) / abs(out[1][2]) < LAM_TOL
-    assert np.abs(out[0][1] - out[1][1]).max() / np.abs(out[1][1]).max() < 1e-4
+    assert np.abs(out[0][1] - out[1][1]).max() / np.abs(out[1][1]).max() < PIX_TOL
 
 
 def test_too_short_sequence_and_bad_arguments_are_errors_not_crashes():
