@@ -43,9 +43,9 @@ sys.path.insert(0, os.path.join(ROOT, "pgure-svt_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIGS = {
-    3: dict(size=512, frames=200, patch=4, traj=15, pgure=False, fps_step=32, crop=256,
+    3: dict(size=512, frames=200, patch=4, traj=15, pgure=False, fps_step=25, crop=256,
             name="configs[2]: synthetic Poisson-Gaussian 512x512x200 uint16, patch 4, trajectory 15, fixed lambda 0.15 (pure SVT path)"),
-    4: dict(size=1024, frames=1000, patch=4, traj=15, pgure=True, fps_step=32, crop=128,
+    4: dict(size=1024, frames=1000, patch=4, traj=15, pgure=True, fps_step=125, crop=128,
             name="configs[3]: synthetic Poisson-Gaussian 1024x1024x1000 uint16, patch 4, trajectory 15, per-frame PGURE lambda search (tol 1e-7)"),
     5: dict(size=4096, frames=500, patch=8, traj=31, pgure=True, fps_step=1, crop=64,
             name="configs[4]: synthetic Poisson-Gaussian 4096x4096x500 uint16, patch 8, trajectory 31 (64x31 Casorati), PGURE lambda + ARPS"),
@@ -188,9 +188,12 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5], help="BASELINE.json workload (see the module docstring)")
     ap.add_argument("--size", type=int, default=None, help="override the frame size of the chosen config (tests)")
     ap.add_argument("--frames-per-step", type=int, default=None,
-                    help="frames of the sequence each GPU denoises per step (plus halo frames each side).  Every step starts cold "
-                         "(halo medians, cold ARPS pairs, cold noise window — what a GPU pays once per job); measured: 125-frame steps "
-                         "(1000 frames / 8 GPUs) give the same frames/s as 32-frame steps, which keep a step at ~1.4 s")
+                    help="frames of the sequence each GPU denoises per step (plus halo frames each side); default: the share of one of "
+                         "8 GPUs of the config's sequence (config 4: 1000 / 8 = 125 frames, a 3.8 s step).  Every step starts cold (halo "
+                         "medians, cold ARPS pairs, cold noise window — what a GPU pays once per job).  The per-frame cost is data-"
+                         "dependent (probes of the lambda search, exact fixes of the lean path), and a step ends when the slowest rank "
+                         "does: with 32-frame blocks the 8 ranks' blocks differ by up to 7 % (243.8 frames/s at N = 8), with 125-frame "
+                         "blocks the differences average out (265.6 frames/s; profiles/r02/bench_8gpu_*.json)")
     ap.add_argument("--noise", default="estimate", choices=["known", "estimate"],
                     help="estimate: alpha/mu/sigma unknown, estimated per frame on the GPU (the reference's default usage); "
                          "known: alpha/mu/sigma supplied (isolates SVD + lambda search)")
@@ -358,8 +361,18 @@ def main():
         kwo.update(device=0, eps1_mode=args.eps1_mode, n_gpus=world)
         h2d, d2h = fsz * 2 * nfr_e2e, fsz * 8 * nfr_e2e + 32 * nfr_e2e
         dt_e2e = 0.0
+        # the sequence of the call: every rank's own block of frames (different data per device, generated in parallel),
+        # concatenated on rank 0 over the host-side group
+        mine = np.ascontiguousarray(np.transpose(Xb[:, :, fb - r0:fb - r0 + fps_step], (2, 1, 0)))  # (frames, cols, rows) C-order
+        if world > 1:
+            tm = torch.from_numpy(mine.view(np.uint8))  # (gloo has no 16-bit integer type: same bytes)
+            parts = [torch.empty_like(tm) for _ in range(world)] if rank == 0 else None
+            dist.gather(tm, parts, dst=0, group=host_group)
+            if rank == 0:
+                mine = torch.cat(parts, dim=0).numpy().view(np.uint16)
         if rank == 0:
-            Xe = make_block(size, nfr_e2e, seed=77)  # pageable numpy, F-order
+            Xe = np.transpose(mine, (2, 1, 0))  # (rows, cols, frames) view, F-contiguous: pageable numpy as a user holds it
+            assert Xe.flags.f_contiguous and Xe.shape == (size, size, nfr_e2e)
             bridge.pguresvt_u16(Xe, **kwo)  # warm-up (contexts on every device, page-locked staging)
             t0 = time.perf_counter()
             for _ in range(args.steps):
