@@ -1,8 +1,30 @@
+"""Small end-to-end runs of every evaluation path for compute-sanitizer (memcheck / racecheck) on the GPU box."""
+import os
 import sys
-sys.path.insert(0,'.'); sys.path.insert(0,'pgure-svt_b200'); sys.path.insert(0,'tests')
-import numpy as np
-from conftest import synthetic_sequence
-from pguresvt import _pguresvt as b
-X,_ = synthetic_sequence(32, 16, seed=123)
-h = b.Handle(X, frame_begin=8, frame_end=9, optimize_pgure=True, lambda1=-1.0, noise_alpha=0.05, noise_mu=0.03, noise_sigma=0.03, random_seed=1)
-h.process(); print(h.stats()); h.close()
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pgure-svt_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+from conftest import synthetic_sequence  # noqa: E402
+from pguresvt import _pguresvt as b  # noqa: E402
+
+X, _ = synthetic_sequence(64, 18, seed=123)
+base = dict(optimize_pgure=True, lambda1=-1.0, random_seed=1)
+for name, env, kw in [("lean top1 (default)", {}, {}), ("tile eval", {"PGURESVT_TILE_EVAL": "1"}, {}),
+                      ("jacobi lean (top1 off)", {"PGURESVT_TOP1": "0"}, {}), ("eps1 mode 1", {}, {"eps1_mode": 1}),
+                      ("compact 64x15", {}, {"patch_size": 8})]:
+    for k, v in env.items():
+        os.environ[k] = v
+    h = b.Handle(X, frame_begin=8, frame_end=10, **base, **kw)
+    h.process()
+    Y, e = h.download()
+    st = h.stats()
+    print(name, "lambda", e[8:10, 0], "evals", st["evals"], "exact", st["lean_exact_svds"], flush=True)
+    h.close()
+    for k in env:
+        os.environ.pop(k)
+Y1, e1, _ = b.pguresvt_u16(X, n_gpus=1, **base)
+print("one-shot", e1[0, :3])
