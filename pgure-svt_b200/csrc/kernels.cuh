@@ -2214,7 +2214,7 @@ __global__ void __launch_bounds__(128, MINB)
             const double *__restrict__ q0, const double *__restrict__ q2, const double *__restrict__ q3,
             const short2 *__restrict__ pos, const int *__restrict__ ids, int P, int vecSize, int N, double lambda, int expw,
             double *__restrict__ acc0, const double *__restrict__ accs, double *__restrict__ partial, int *__restrict__ kpart,
-            int qmax, int *__restrict__ need_more_q)
+            int qmax, int *__restrict__ need_more_q, int tiled)
 {
     // One PGURE evaluation for 16 x 15 patches and the three SVT objects U, U +- eps2*delta2.  16 lanes per patch; lane g
     // owns block row g (pixel (g&3, g>>2) of the patch) for all 15 slices and thresholds slot g of every object.
@@ -2399,7 +2399,11 @@ __global__ void __launch_bounds__(128, MINB)
             for (int k = 0; k < SVD16_N; k++)
             {
                 const short2 p = sp[k];
-                acc_add(acc0, (size_t)((p.x + r) + N * (p.y + c) + fsz * k), a0[k], ascale);
+                // tiled accumulator (N even): every 2 x 2 pixel block is one 32-byte sector, so a 4 x 4 footprint at a random
+                // offset touches 6.25 sectors on average instead of 7 (four columns x 1.75) — the kernel is bound by RED sectors
+                const int row = p.x + r, col = p.y + c;
+                const int idx = tiled ? 4 * ((row >> 1) + (N >> 1) * (col >> 1)) + (row & 1) + 2 * (col & 1) : row + N * col;
+                acc_add(acc0, (size_t)(idx + fsz * k), a0[k], ascale);
             }
             s4tot += s4;
         }
@@ -2456,15 +2460,22 @@ __global__ void __launch_bounds__(128)
 // partial: gridDim.x * 4 doubles (s1, s5, s4, triplets streamed)
 __global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
                             const double *__restrict__ accs, const double *__restrict__ s4part, const int *__restrict__ kpart, int ns4,
-                            double *__restrict__ partial)
+                            double *__restrict__ partial, int tiledN = 0)
 {
     double s1 = 0, s5 = 0, s4 = 0, sk = 0;
     const double ainv = __ldg(accs + 1);
+    const unsigned N_ = (unsigned)tiledN, fsz_ = N_ * N_, hN = N_ >> 1;
     // (an unrolled variant with more loads in flight per thread needs 58 registers, halves the resident CTAs and is slower)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
     {
-        const double v0 = norm_or_zero(acc_val(acc0, i, ainv), cnt[i]);
-        acc0[i] = 0.0;
+        size_t ia = i;
+        if (tiledN)
+        { // accumulator in the 2 x 2-tiled layout of k_eval3 (weights and u stay in image order)
+            const unsigned iu = (unsigned)i, k = iu / fsz_, rem = iu - k * fsz_, col = rem / N_, row = rem - col * N_;
+            ia = (size_t)k * fsz_ + 4u * ((row >> 1) + hN * (col >> 1)) + (row & 1u) + 2u * (col & 1u);
+        }
+        const double v0 = norm_or_zero(acc_val(acc0, ia, ainv), cnt[i]);
+        acc0[ia] = 0.0;
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
         s5 += v0;

@@ -1600,16 +1600,18 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
     {
         static const int ppg = getenv("PGURESVT_EVAL_PPG") ? atoi(getenv("PGURESVT_EVAL_PPG")) : EVAL_PPG;
         const bool lean_now = h->lean && !h->frame_full;
+        static const bool tiled_off = getenv("PGURESVT_ACC_TILED") && atoi(getenv("PGURESVT_ACC_TILED")) == 0;
+        const int tiled = (h->N % 2 == 0 && !tiled_off) ? 1 : 0;
         auto kev = lean_now ? k_eval3<6, 8, 1>
                             : (ppg == 1) ? k_eval3<6, 1, 0> : (ppg == 4) ? k_eval3<6, 4, 0> : (ppg == 16) ? k_eval3<6, 16, 0> : (ppg == 32) ? k_eval3<6, 32, 0> : k_eval3<6, 8, 0>;
         const int ppg_eff = lean_now ? 8 : (ppg == 1 || ppg == 4 || ppg == 16 || ppg == 32) ? ppg : 8;
         // (lean: the head records travel in the q0 argument; fac2/fac3/q2/q3 are not read)
         kev<<<cdiv(h->P, 8 * ppg_eff), 128, 0, h->st>>>(h->dFac[0], h->dFac[2], h->dFac[3], lean_now ? h->dHead : h->dQ[0], h->dQ[1], h->dQ[2],
                                                         h->dPos, h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
-                                                        h->p.exp_weighting, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->q_k, h->dNeedQ);
+                                                        h->p.exp_weighting, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->q_k, h->dNeedQ, tiled);
         LAUNCHED(h);
         k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
-                                                    4 * cdiv(h->P, 8 * ppg_eff), h->dPartial);
+                                                    4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0);
         LAUNCHED(h);
         k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
         LAUNCHED(h);
