@@ -212,6 +212,10 @@ int64_t pguresvt_host_patch_ids(uint32_t N, uint32_t bs, uint32_t bo, int32_t *o
 int pguresvt_host_plan_gpus(const pguresvt_params *p, uint32_t n_frames, int n_visible);
 int pguresvt_host_frame_block(uint32_t n_frames, int parts, int part, uint32_t *begin, uint32_t *end);
 
+/* out (n_rows, n_cols, n_frames) C-order = in (n_frames, n_cols, n_rows) C-order with the axes reversed: the copy
+ * pguresvt/svt.py:329 makes of the bridge's result, cache-blocked over host threads (n_threads <= 0: automatic). */
+int pguresvt_host_transpose_f64(const double *in, uint32_t n_frames, uint32_t n_cols, uint32_t n_rows, double *out, int n_threads);
+
 /* Measured FP64 DFMA throughput of the device's vector pipe in TFLOP/s (burst = best single launch, sustained = ~1 s back
  * to back): the roofline denominator of the SVD kernels, taken in the same job as the bench (bench.py). */
 int pguresvt_bench_dfma(int device, double *tflops_burst, double *tflops_sustained);

@@ -2619,6 +2619,45 @@ extern "C" int pguresvt_host_sbplx(double (*f)(double, void *), void *data, doub
     return st;
 }
 
+// out[r][c][f] = in[f][c][r]: the axis reversal svt.py:329 applies to the bridge's (frames, cols, rows) result
+// (`np.transpose(X, (2, 1, 0))` made contiguous), cache-blocked and spread over host threads — numpy's strided copy moves
+// ~0.3 GB/s, which made SVT.denoise a third slower than the call underneath it.
+extern "C" int pguresvt_host_transpose_f64(const double *in, uint32_t nf, uint32_t nc, uint32_t nr, double *out, int n_threads)
+{
+    if (!in || !out)
+        return fail(PGS_ERR_ARG, "null argument");
+    if (n_threads <= 0)
+        n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t B = 32;
+    auto work = [&](uint32_t c0, uint32_t c1) {
+        for (uint32_t c = c0; c < c1; c++)
+            for (uint32_t fb = 0; fb < nf; fb += B)
+                for (uint32_t rb = 0; rb < nr; rb += B)
+                {
+                    const uint32_t fe = std::min(nf, fb + B), re = std::min(nr, rb + B);
+                    for (uint32_t r = rb; r < re; r++)
+                    {
+                        double *o = out + ((size_t)r * nc + c) * nf;
+                        const double *i0 = in + (size_t)c * nr + r;
+                        for (uint32_t f = fb; f < fe; f++)
+                            o[f] = i0[(size_t)f * nc * nr];
+                    }
+                }
+    };
+    n_threads = (int)std::min<uint32_t>((uint32_t)n_threads, std::max(1u, nc));
+    std::vector<std::thread> th;
+    const uint32_t per = (nc + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++)
+    {
+        const uint32_t c0 = std::min(nc, (uint32_t)t * per), c1 = std::min(nc, c0 + per);
+        if (c0 < c1)
+            th.emplace_back(work, c0, c1);
+    }
+    for (auto &t : th)
+        t.join();
+    return PGS_OK;
+}
+
 // number of patches and the sorted patch-id set of SVT::Decompose (svt.hpp:61-97) — host logic, no GPU needed
 extern "C" int64_t pguresvt_host_patch_ids(uint32_t N, uint32_t bs, uint32_t bo, int32_t *out, int64_t cap)
 {

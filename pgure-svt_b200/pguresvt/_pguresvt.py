@@ -103,6 +103,7 @@ def load():
     L.pguresvt_probe_window_sum.argtypes = [vp, u32, dp]
     L.pguresvt_hotpixel_u16.argtypes = [C.POINTER(C.c_uint16), u32, u32, u32, C.c_double, C.c_int]
     L.pguresvt_bench_dfma.argtypes = [C.c_int, dp, dp]
+    L.pguresvt_host_transpose_f64.argtypes = [dp, u32, u32, u32, dp, C.c_int]
     L.pguresvt_device_info.argtypes = [C.c_int, C.c_char_p, C.c_int]
     L.pguresvt_host_patch_ids.argtypes = [u32, u32, u32, C.POINTER(C.c_int32), C.c_int64]
     L.pguresvt_host_patch_ids.restype = C.c_int64
@@ -120,6 +121,17 @@ def frame_block(n_frames, parts, part):
     b, e = C.c_uint32(0), C.c_uint32(0)
     check(load().pguresvt_host_frame_block(int(n_frames), int(parts), int(part), C.byref(b), C.byref(e)), "frame_block")
     return b.value, e.value
+
+
+def reversed_axes_copy(X):
+    """C-contiguous copy of `np.transpose(X, (2, 1, 0))` for a C-contiguous float64 (frames, cols, rows) array — what svt.py:329
+    does with the bridge's result, through the library's threaded blocked transpose."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    nf, nc, nr = X.shape
+    out = np.empty((nr, nc, nf), dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    check(load().pguresvt_host_transpose_f64(X.ctypes.data_as(dp), nf, nc, nr, out.ctypes.data_as(dp), 0), "transpose")
+    return out
 
 
 def release_cached():

@@ -6,6 +6,7 @@ unchanged; the numerics happen in libpguresvt_b200.so.
 import numpy as np
 
 from ._pguresvt import pguresvt_d, pguresvt_f, pguresvt_u8, pguresvt_u16
+from ._pguresvt import reversed_axes_copy as _reversed_axes_copy
 
 _ENTRY_POINTS = {
     np.dtype("uint8"): pguresvt_u8,
@@ -201,6 +202,6 @@ class SVT:
         )
 
         # bridge output is (frames, cols, rows): transpose back to the caller's axis order, C-contiguous
-        self.Y_ = np.ascontiguousarray(np.transpose(Xd, (2, 1, 0)))
+        self.Y_ = _reversed_axes_copy(Xd)
         self.lambda1s_, self.noise_alphas_, self.noise_mus_, self.noise_sigmas_ = (estimates[i] for i in range(4))
         return self

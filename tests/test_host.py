@@ -282,3 +282,12 @@ def test_plan_gpus_and_frame_blocks_match_reference_partition():
     for n, w in [(16, 2), (17, 2), (1000, 8), (5, 8), (23, 4)]:
         for r in range(w):
             assert bridge.frame_block(n, w, r) == frame_block(r, w, n)
+
+
+def test_threaded_transpose_equals_numpy():
+    """svt.py:329 reverses the axes of the bridge's result; the library's blocked, threaded copy must equal numpy's."""
+    rng = np.random.RandomState(0)
+    for shape in [(16, 32, 32), (17, 33, 21), (1, 5, 7), (40, 64, 48)]:
+        X = rng.rand(*shape)
+        out = bridge.reversed_axes_copy(X)
+        assert out.flags.c_contiguous and np.array_equal(out, np.transpose(X, (2, 1, 0)))
