@@ -1089,10 +1089,11 @@ static int noise_analyse_batch(NoiseWorkspace &ws, const double *dU, int N, cons
         const int *a3 = dBig;
         double *a5 = ws.dScratch, *a6 = ws.dLeaf;
         void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&a4, (void *)&a5, (void *)&a6, (void *)&gs};
-        // steady state (one new slice per frame): a quarter of the SMs, like the line fit; a cold window (many whole-frame
-        // regions back to back) is throughput-bound and takes the whole grid
+        // the whole grid (round 1 gave the steady-state case a quarter of the SMs so that the long Jacobi launches kept their
+        // CTAs; beside the 2.3-ms dominant-triplet launches of round 2 the estimate itself became the exposed part: measured
+        // 32.2 -> 33.9 frames/s, profiles/r02/noise_grid_sweep.txt)
         static const int big_div_env = getenv("PGURESVT_BIG_GRID_DIV") ? atoi(getenv("PGURESVT_BIG_GRID_DIV")) : 0;
-        const int big_div = big_div_env > 0 ? big_div_env : (lbig.size() > 4 ? 1 : 4);
+        const int big_div = big_div_env > 0 ? big_div_env : 1;
         NCU(cudaLaunchCooperativeKernel((void *)k_noise_big<512>, dim3(std::max(1, ws.grid / big_div)), dim3(512), args, 0, st));
         if (launches)
             (*launches)++;
@@ -1218,9 +1219,9 @@ static int noise_estimate_window(NoiseWorkspace &ws, const double *dU, int N, in
         int a2 = (int)n;
         double *a3 = ws.dFit;
         void *args[] = {(void *)&a0, (void *)&a1, (void *)&a2, (void *)&a3, (void *)&gs};
-        // a quarter of the SMs: the fit is bound by its ~290 grid-wide barriers, which get cheaper with fewer CTAs, and the
+        // a third of the SMs: the fit is bound by its ~290 grid-wide barriers, which get cheaper with fewer CTAs, and the
         // other three quarters keep both of their SVD CTAs while it runs (measured +2.3 % frames/s against one CTA per SM)
-        static const int wls_div = getenv("PGURESVT_WLS_GRID_DIV") ? atoi(getenv("PGURESVT_WLS_GRID_DIV")) : 4;
+        static const int wls_div = getenv("PGURESVT_WLS_GRID_DIV") ? atoi(getenv("PGURESVT_WLS_GRID_DIV")) : 3;
         NCU(cudaLaunchCooperativeKernel((void *)k_noise_wls_grid<512>, dim3(std::max(1, ws.grid / wls_div)), dim3(512), args, 0, st));
         if (launches)
             (*launches)++;
