@@ -47,3 +47,30 @@ def test_tiff_reader_matches_opencv_and_roundtrips(tmp_path):
     ok, pages2 = cv2.imreadmulti(dst, flags=cv2.IMREAD_UNCHANGED)
     assert ok and len(pages2) == len(pages)
     assert all(np.array_equal(a, b) for a, b in zip(pages, pages2))
+
+
+def test_cli_rejects_pages_of_different_size_and_empty_tags(tmp_path):
+    """the TIFF reader trusted page 0's geometry for every page and indexed v[0] of zero-count tags."""
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(ROOT, "pgure-svt_b200", "PGURE-SVT")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    rng = np.random.RandomState(0)
+    pages = [rng.randint(0, 1000, (32, 32)).astype(np.uint16) for _ in range(16)] + [rng.randint(0, 1000, (16, 16)).astype(np.uint16)]
+    assert cv2.imwritemulti(str(tmp_path / "mixed.tif"), pages, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+    (tmp_path / "p.svt").write_text("filename : ./mixed.tif\nstart_frame : 1\nend_frame : 17\noptimize_pgure : false\nlambda : 0.1\n")
+    r = subprocess.run([exe, "p.svt"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "page 17 is 16x16" in (r.stdout + r.stderr)
+    # a tag with a zero value count (ImageWidth, count 0) is refused by the reader instead of read out of bounds
+    raw = bytearray((tmp_path / "mixed.tif").read_bytes())
+    import struct
+
+    ifd = struct.unpack_from("<I", raw, 4)[0]
+    nent = struct.unpack_from("<H", raw, ifd)[0]
+    for e in range(nent):
+        off = ifd + 2 + 12 * e
+        if struct.unpack_from("<H", raw, off)[0] == 256:
+            struct.pack_into("<I", raw, off + 4, 0)
+    (tmp_path / "bad.tif").write_bytes(bytes(raw))
+    r = subprocess.run([TOOL, "tiffinfo", str(tmp_path / "bad.tif")], capture_output=True, text=True)
+    assert r.returncode != 0
