@@ -631,6 +631,22 @@ __global__ void __launch_bounds__(128)
 }
 
 // reference coordinates of the window's reference slice (arps.hpp:60-64)
+// up to 32 trajectory slices copied in ONE launch (cached ARPS pairs into the window's trajectory array and back): a frame
+// moves ~14 slices of 4 MB, and 14 cudaMemcpyAsync calls cost more in launch gaps than the 56 MB cost in bandwidth
+struct SliceCopies
+{
+    const int *src[32];
+    int *dst[32];
+    int n;
+};
+__global__ void k_copy_slices(SliceCopies sc, int words)
+{
+    const int *s = sc.src[blockIdx.y];
+    int *d = sc.dst[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+
 __global__ void k_seed_pos(short2 *__restrict__ pos, int vecSize, int M1, int ref)
 {
     const int it = blockIdx.x * blockDim.x + threadIdx.x;

@@ -121,6 +121,7 @@ struct pguresvt_handle
         double wmax = 0;
     };
     std::vector<ArpsTag> tagF, tagB;
+    SliceCopies pend{}; // trajectory slice copies waiting for one k_copy_slices launch
     int arps_ring = 0;
     int *dIds = nullptr;
     unsigned *dCnt = nullptr;
@@ -1064,6 +1065,30 @@ static void arps_pair(pguresvt_handle *h, int f1, int f2, const short2 *pred, sh
 // is independent of the output frame it is run for, as long as the window normalisation wMax is bit-identical
 // (the block cost is evaluated on w = z / wMax, and ties decide vectors).  Forward results are keyed by the target
 // frame g (source g-1), backward results by target g (source g+1).
+static int flush_slice_copies(pguresvt_handle *h)
+{
+    if (h->pend.n == 0)
+        return PGS_OK;
+    k_copy_slices<<<dim3(std::min(cdiv(h->vecSize, 256), 64), h->pend.n), 256, 0, h->st>>>(h->pend, h->vecSize); // short2 = one 32-bit word
+    LAUNCHED(h);
+    h->pend.n = 0;
+    CU(cudaGetLastError());
+    return PGS_OK;
+}
+static int queue_slice_copy(pguresvt_handle *h, const short2 *src, short2 *dst)
+{
+    if (h->pend.n == 32)
+    {
+        int rc = flush_slice_copies(h);
+        if (rc)
+            return rc;
+    }
+    h->pend.src[h->pend.n] = reinterpret_cast<const int *>(src);
+    h->pend.dst[h->pend.n] = reinterpret_cast<int *>(dst);
+    h->pend.n++;
+    return PGS_OK;
+}
+
 static int arps_cached_pair(pguresvt_handle *h, bool forward, int src_local, int tgt_local)
 {
     const long long g = (long long)h->cur_a + tgt_local;
@@ -1073,21 +1098,20 @@ static int arps_cached_pair(pguresvt_handle *h, bool forward, int src_local, int
     short2 *dst = h->dPos + (size_t)tgt_local * h->vecSize;
     if (tag.frame == g && tag.wmax == h->cur_wMax)
     {
-        CU(cudaMemcpyAsync(dst, cache, (size_t)h->vecSize * sizeof(short2), cudaMemcpyDeviceToDevice, h->st));
         h->stats[15] += 1;
-        return PGS_OK;
+        return queue_slice_copy(h, cache, dst);
     }
-    arps_pair(h, src_local, tgt_local, nullptr, dst);
-    CU(cudaMemcpyAsync(cache, dst, (size_t)h->vecSize * sizeof(short2), cudaMemcpyDeviceToDevice, h->st));
+    arps_pair(h, src_local, tgt_local, nullptr, dst); // (zero predictor: reads no trajectory slice, so queued copies may wait)
     tag.frame = g;
     tag.wmax = h->cur_wMax;
-    return PGS_OK;
+    return queue_slice_copy(h, dst, cache); // (stream order: the copy kernel is launched after this pair's kernel)
 }
 
 static int stage_motion(pguresvt_handle *h, uint32_t t) // MotionEstimator::Estimate, arps.hpp:52-134
 {
     const int tw = (int)h->fw, Ntw = (int)h->win, nImages = (int)h->nframes, ti = (int)t;
     const int ref = h->cur_ref;
+    h->pend.n = 0;
     CU(cudaMemsetAsync(h->dNcost, 0, sizeof(unsigned long long), h->st));
     if (!h->p.motion_estimation)
     { // only the reference slice is populated; every other slice stays (0,0)
@@ -1126,11 +1150,17 @@ static int stage_motion(pguresvt_handle *h, uint32_t t) // MotionEstimator::Esti
     for (int i = 0; i < nbwd; i++)
     {
         if (i == 0 && nfwd > 0 && !special)
-            // predictor = the vector the first forward pair found for the same block; specific to this frame
+        { // predictor = the vector the first forward pair found for the same block; specific to this frame.
+          // It reads trajectory slice ref + 1: the queued copies must have landed.
+            if ((rc = flush_slice_copies(h)))
+                return rc;
             arps_pair(h, ref, ref - 1, h->dPos + (size_t)(ref + 1) * h->vecSize, h->dPos + (size_t)(ref - 1) * h->vecSize);
+        }
         else if ((rc = arps_cached_pair(h, false, ref - i, ref - i - 1)))
             return rc;
     }
+    if ((rc = flush_slice_copies(h)))
+        return rc;
     // slices no pair targets stay (0,0) like the zero-initialised icube (arps.hpp:42); with a full schedule none is left
     for (int k = 0; k < Ntw; k++)
         if (k > ref + nfwd || k < ref - nbwd)
