@@ -2258,7 +2258,17 @@ __global__ void __launch_bounds__(128, MINB)
             pidx = P - 1;
         const size_t roff = (size_t)SVD16_REC * pidx;
         double *dst = sg + st * EV_STAGE;
-        if (LEAN)
+        if (LEAN == 2)
+        { // accumulate-only pass over ONE object (eps1_mode 1: object U1): its S, U and V column 0
+            if (g < 8)
+            {
+                cp_async16(dst + 0 + 2 * g, fac0 + roff + soff + 2 * g);
+                cp_async16(dst + 96 + 2 * g, fac0 + roff + 2 * g);
+            }
+            else
+                cp_async16(dst + 112 + 2 * (g - 8), fac0 + roff + SVD16_M * SVD16_N + 2 * (g - 8));
+        }
+        else if (LEAN)
         { // head record (q0 carries it in this mode), U and V column 0 of object U
             if (g < 8)
             {
@@ -2312,7 +2322,12 @@ __global__ void __launch_bounds__(128, MINB)
         const double *ss = sg + st * EV_STAGE;
         const short2 *sp = reinterpret_cast<const short2 *>(ss + 128);
         double f0 = 0.0, s4 = 0.0;
-        if (LEAN)
+        if (LEAN == 2)
+        {
+            if (g < SVD16_N)
+                f0 = soft_f(ss[g], ss[15], lambda, expw);
+        }
+        else if (LEAN)
         {
             if (g < 3)
             {
@@ -2429,7 +2444,7 @@ __global__ void __launch_bounds__(128, MINB)
     cp_async_wait<0>();
     // per-warp partials (no CTA barrier): partial[4 * blockIdx.x + warp] = s4 part, kpart[...] = triplets fetched
     s4tot = warp_sum(s4tot);
-    if (lane == 0)
+    if (lane == 0 && LEAN != 2)
     {
         const int w = 4 * blockIdx.x + (threadIdx.x >> 5);
         partial[w] = s4tot;
@@ -2476,9 +2491,13 @@ __global__ void __launch_bounds__(128)
 // partial: gridDim.x * 4 doubles (s1, s5, s4, triplets streamed)
 __global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__ u, const unsigned *__restrict__ cnt, double *__restrict__ acc0, size_t tot,
                             const double *__restrict__ accs, const double *__restrict__ s4part, const int *__restrict__ kpart, int ns4,
-                            double *__restrict__ partial, int tiledN = 0)
+                            double *__restrict__ partial, int tiledN = 0, double *__restrict__ acc1 = nullptr,
+                            const int8_t *__restrict__ d1 = nullptr, double e_alpha = 0.0, double e_const = 0.0,
+                            double *__restrict__ partial3 = nullptr)
 {
-    double s1 = 0, s5 = 0, s4 = 0, sk = 0;
+    // acc1 != nullptr (eps1_mode 1): third sum of pgure.hpp:136, s3 = sum delta1 (alpha U - alpha mu + sigma^2)(U1 - Uhat), with
+    // U1's accumulator filled by the accumulate-only pass of k_eval3; e_alpha = alpha, e_const = sigma^2 - alpha mu
+    double s1 = 0, s5 = 0, s4 = 0, sk = 0, s3 = 0;
     const double ainv = __ldg(accs + 1);
     const unsigned N_ = (unsigned)tiledN, fsz_ = N_ * N_, hN = N_ >> 1;
     // (an unrolled variant with more loads in flight per thread needs 58 registers, halves the resident CTAs and is slower)
@@ -2495,34 +2514,47 @@ __global__ void __launch_bounds__(256, 8) k_risk_uhat(const double *__restrict__
         const double d = v0 - u[i];
         s1 = fma(d, d, s1);
         s5 += v0;
+        if (acc1)
+        {
+            const double v1 = norm_or_zero(acc_val(acc1, ia, ainv), cnt[i]);
+            acc1[ia] = 0.0;
+            s3 += ((double)d1[i] * (e_alpha * u[i] + e_const)) * (v1 - v0);
+        }
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns4; i += gridDim.x * blockDim.x)
     {
         s4 += s4part[i];
         sk += (double)kpart[i];
     }
-    __shared__ double sm[4][32];
+    __shared__ double sm[5][32];
     s1 = warp_sum(s1);
     s5 = warp_sum(s5);
     s4 = warp_sum(s4);
     sk = warp_sum(sk);
+    s3 = warp_sum(s3);
     if ((threadIdx.x & 31) == 0)
     {
         sm[0][threadIdx.x >> 5] = s1;
         sm[1][threadIdx.x >> 5] = s5;
         sm[2][threadIdx.x >> 5] = s4;
         sm[3][threadIdx.x >> 5] = sk;
+        sm[4][threadIdx.x >> 5] = s3;
     }
     __syncthreads();
     if (threadIdx.x < 32)
     {
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 5; q++)
         {
             double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[q][threadIdx.x] : 0.0;
             r = warp_sum(r);
             if (threadIdx.x == 0)
-                partial[(size_t)blockIdx.x * 4 + q] = r;
+            {
+                if (q < 4)
+                    partial[(size_t)blockIdx.x * 4 + q] = r;
+                else if (partial3)
+                    partial3[blockIdx.x] = r;
+            }
         }
     }
 }

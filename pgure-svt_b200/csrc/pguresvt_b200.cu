@@ -80,6 +80,9 @@ struct pguresvt_handle
     bool use_fused_eval = false;
     bool lean = false;           // fused path: perturbed objects leave only head entries behind (k_svd16_l4 EPI 1), no q-form pass
     bool frame_full = false;     // lean mode: the current frame has been decomposed in full after all (a third triplet survived)
+    bool eps1f = false;          // eps1_mode 1 through the fused evaluation (object U and U1 exact, U2p / U2m lean)
+    double *dPartial3 = nullptr; // eps1f: per-block partials of s3
+    bool acc1_clean = false;
     bool top1_all = false;       // top1 for object U as well (bound from the Gram matrix): no Jacobi launch in the common case
     bool top1 = false;           // lean mode: perturbed objects by k_top1_l4 (dominant triplet + rigorous bound), exact on demand
     double *dUp3 = nullptr;      // top1: perturbed window of object U2m (dUp keeps U2p's)
@@ -297,7 +300,7 @@ static void free_all(pguresvt_handle *h)
     if (h->hSum2)
         cudaFreeHost(h->hSum2);
     F(h->dSum2);
-    F(h->dUp3), F(h->dLeanList), F(h->dCrit);
+    F(h->dUp3), F(h->dLeanList), F(h->dCrit), F(h->dPartial3);
     if (h->hLean)
         cudaFreeHost(h->hLean);
     F(h->dBinCnt), F(h->dBinStart), F(h->dScanSums), F(h->dEnt), F(h->dHead), F(h->dTilePart), F(h->dFth), F(h->dU0c);
@@ -392,10 +395,13 @@ static int create_impl(pguresvt_handle *h)
     if (p.svd_kernel >= 2 && !h->use_reg_svd)
         return fail(PGS_ERR_UNSUPPORTED, "register SVD kernels only cover 16x15 Casorati matrices");
     h->use_l4 = h->use_reg_svd && p.svd_kernel != 2; // 0 / 3: 4-lane kernel with tracked / recomputed pair norms
-    h->use_fused_eval = h->use_l4 && p.optimize_pgure && p.eps1_mode == 0;
+    // eps1_mode 1 (4 SVT objects): fused evaluation too, with object U1 decomposed exactly and overlap-added by an accumulate-only
+    // pass (k_eval3<..., 2>) and the first-order sum s3 taken in the voxel pass; PGURESVT_EPS1_FUSED=0 keeps the generic path
+    h->eps1f = h->use_l4 && p.optimize_pgure && p.eps1_mode == 1 && !(getenv("PGURESVT_EPS1_FUSED") && atoi(getenv("PGURESVT_EPS1_FUSED")) == 0);
+    h->use_fused_eval = h->use_l4 && p.optimize_pgure && (p.eps1_mode == 0 || h->eps1f);
     h->lean = h->use_fused_eval && !(getenv("PGURESVT_LEAN") && atoi(getenv("PGURESVT_LEAN")) == 0);
     h->top1 = h->lean && !(getenv("PGURESVT_TOP1") && atoi(getenv("PGURESVT_TOP1")) == 0);
-    h->top1_all = h->top1 && !(getenv("PGURESVT_TOP1_ALL") && atoi(getenv("PGURESVT_TOP1_ALL")) == 0);
+    h->top1_all = h->top1 && !h->eps1f && !(getenv("PGURESVT_TOP1_ALL") && atoi(getenv("PGURESVT_TOP1_ALL")) == 0);
     h->use_warp_svd = (h->m == 64 && h->n <= 32 && p.svd_kernel != 1);
     // rank_cache: 0 = automatic, > 0 = that many leading triplets, < 0 = keep the full factor cache (generic path)
     h->use_compact = !h->use_l4 && p.optimize_pgure && p.eps1_mode == 0 && p.rank_cache >= 0;
@@ -416,10 +422,10 @@ static int create_impl(pguresvt_handle *h)
       // the generic shared-memory SVD — slower, but it runs (default-parameter sequences at 4096^2).
         size_t freeb = 0, totb = 0;
         CU(cudaMemGetInfo(&freeb, &totb));
-        const size_t need = h->rec * (size_t)h->P * sizeof(double) * (h->lean ? 1 : h->nobj) + wtot * 60 + h->fsz * ((size_t)nres * (h->esz + 2) + (size_t)nblk * 8);
+        const size_t need = h->rec * (size_t)h->P * sizeof(double) * (h->lean ? (h->eps1f ? 2 : 1) : h->nobj) + wtot * 60 + h->fsz * ((size_t)nres * (h->esz + 2) + (size_t)nblk * 8);
         if (need > freeb - freeb / 10)
         {
-            h->use_l4 = h->use_reg_svd = h->use_fused_eval = h->lean = false;
+            h->use_l4 = h->use_reg_svd = h->use_fused_eval = h->lean = h->eps1f = false;
             h->use_compact = p.eps1_mode == 0;
             if (!h->use_compact)
                 return fail(PGS_ERR_UNSUPPORTED, "the SVD factors of %d patches x %d objects (%.1f GB) do not fit on device %d (%.1f GB free)", h->P,
@@ -469,7 +475,7 @@ static int create_impl(pguresvt_handle *h)
     for (int k = 0; k < h->nobj; k++)
     {
         const int o = h->objs[k];
-        if (o == 0 || !(h->use_fused_eval || h->use_compact))
+        if (o == 0 || (o == 1 && h->eps1f) || !(h->use_fused_eval || h->use_compact))
             CU(cudaMalloc(&h->dAcc[o], wtot * sizeof(double)));
         if (h->use_compact)
         {
@@ -479,7 +485,7 @@ static int create_impl(pguresvt_handle *h)
             CU(cudaMemset(h->dQc[o], 0, (size_t)32 * h->P * sizeof(double)));
             continue;
         }
-        if (h->lean && o != 0)
+        if (h->lean && o != 0 && !(o == 1 && h->eps1f))
             continue; // perturbed objects leave head entries only; full records on demand (stage_svd)
         CU(cudaMalloc(&h->dFac[o], h->rec * (size_t)h->P * sizeof(double)));
         CU(cudaMemset(h->dFac[o], 0, h->rec * (size_t)h->P * sizeof(double)));
@@ -505,6 +511,8 @@ static int create_impl(pguresvt_handle *h)
                 CU(cudaMalloc(&h->dQ[k], (size_t)16 * h->P * sizeof(double)));
         CU(cudaMalloc(&h->dHead, (size_t)TG_HEAD * h->P * sizeof(double)));
         CU(cudaMemset(h->dHead, 0, (size_t)TG_HEAD * h->P * sizeof(double)));
+        if (h->eps1f)
+            CU(cudaMalloc(&h->dPartial3, (size_t)RISK_BLOCKS * sizeof(double)));
         if (h->top1)
         {
             CU(cudaMalloc(&h->dUp3, wtot * sizeof(double)));
@@ -515,7 +523,7 @@ static int create_impl(pguresvt_handle *h)
         // the atomics-free gather evaluation (tile_eval.cuh) is exact and deterministic too, but on B200 its irregular gather costs
         // more instructions than the L2 atomic unit costs time: 1.0 ms against 0.55 ms per evaluation at 1024^2 (profiles/r02) —
         // opt-in with PGURESVT_TILE_EVAL=1
-        h->use_tile = getenv("PGURESVT_TILE_EVAL") && atoi(getenv("PGURESVT_TILE_EVAL")) > 0;
+        h->use_tile = !h->eps1f && getenv("PGURESVT_TILE_EVAL") && atoi(getenv("PGURESVT_TILE_EVAL")) > 0;
         if (h->use_tile)
         {
             const size_t nbins = h->fsz * h->win;
@@ -1249,7 +1257,7 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
         // 4: tracked norms with full rotations; 0 (default): tracked norms with fast (scaled) rotations
         const int variant = h->p.svd_kernel == 3 ? 0 : h->p.svd_kernel == 4 ? 1 : 2;
         // epilogue: lean mode leaves head entries (+ the full record of object U); see k_svd16_l4
-        const int epi = !h->lean ? 0 : (obj == 0 ? 2 : (h->full_mode ? 0 : 1));
+        const int epi = (!h->lean || obj == 1) ? 0 : (obj == 0 ? 2 : (h->full_mode ? 0 : 1)); // (object U1: always the full record)
         auto cold = epi == 2 ? (variant == 2 ? k_svd16_l4<0, 2, 2> : variant == 1 ? k_svd16_l4<0, 1, 2> : k_svd16_l4<0, 0, 2>)
                              : (variant == 2 ? k_svd16_l4<0, 2, 0> : variant == 1 ? k_svd16_l4<0, 1, 0> : k_svd16_l4<0, 0, 0>);
         auto warm = epi == 1 ? (variant == 2 ? k_svd16_l4<1, 2, 1> : variant == 1 ? k_svd16_l4<1, 1, 1> : k_svd16_l4<1, 0, 1>)
@@ -1272,7 +1280,7 @@ static int stage_svd(pguresvt_handle *h, int obj) // SVT::Decompose, svt.hpp:58-
             }
             usrc = dst;
         }
-        if (h->top1 && !h->full_mode && (obj != 0 || h->top1_all))
+        if (h->top1 && !h->full_mode && (obj >= 2 || (obj == 0 && h->top1_all)))
         { // dominant triplet + bound instead of the full decomposition (k_top1_l4)
             auto ktop = obj == 0 ? k_top1_l4<2> : h->top1_all ? k_top1_l4<1> : k_top1_l4<0>;
             ktop<<<cdiv(nthreads, 128), 128, 0, h->st>>>(usrc, h->dPos, h->dIds, h->P, h->vecSize, h->N, h->dFac[0], h->dD2, pt.eps, h->d2Neg,
@@ -1493,6 +1501,8 @@ static int launch_recon(pguresvt_handle *h, int obj, double lambda, int only_k) 
 {
     if (obj == 0)
         h->acc0_clean = false;
+    if (obj == 1)
+        h->acc1_clean = false;
     if (h->use_compact)
     {
         if (obj != 0)
@@ -1621,11 +1631,17 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
         CU(cudaMemsetAsync(h->dAcc[0], 0, wtot * sizeof(double), h->st));
         h->acc0_clean = true;
     }
+    if (h->eps1f && !h->acc1_clean)
+    {
+        CU(cudaMemsetAsync(h->dAcc[1], 0, wtot * sizeof(double), h->st));
+        h->acc1_clean = true;
+    }
     {
         int rcf = lean_fix(h, lambda);
         if (rcf)
             return rcf;
     }
+    const double sigmasq_e = sigma * sigma;
     for (int attempt = 0; attempt < 2; attempt++)
     {
         static const int ppg = getenv("PGURESVT_EVAL_PPG") ? atoi(getenv("PGURESVT_EVAL_PPG")) : EVAL_PPG;
@@ -1640,12 +1656,29 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
                                                         h->dPos, h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
                                                         h->p.exp_weighting, h->dAcc[0], h->dAccScale, h->dPartialE, h->dKpart, h->q_k, h->dNeedQ, tiled);
         LAUNCHED(h);
-        k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
-                                                    4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0);
-        LAUNCHED(h);
+        if (h->eps1f)
+        { // object U1 = U + eps1*delta1: accumulate-only pass into its own accumulator, s3 in the voxel pass
+            k_eval3<6, 8, 2><<<cdiv(h->P, 64), 128, 0, h->st>>>(h->dFac[1], nullptr, nullptr, nullptr, nullptr, nullptr, h->dPos,
+                                                                 h->P == h->vecSize ? nullptr : h->dIds, h->P, h->vecSize, h->N, lambda,
+                                                                 h->p.exp_weighting, h->dAcc[1], h->dAccScale, nullptr, nullptr, SVD16_N, nullptr,
+                                                                 tiled);
+            LAUNCHED(h);
+            k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
+                                                        4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0, h->dAcc[1], h->dD1,
+                                                        alpha, sigmasq_e - alpha * mu, h->dPartial3);
+            LAUNCHED(h);
+            k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial3, RISK_BLOCKS, 1, h->dOut + 5);
+            LAUNCHED(h);
+        }
+        else
+        {
+            k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
+                                                        4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0);
+            LAUNCHED(h);
+        }
         k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
         LAUNCHED(h);
-        CU(cudaMemcpyAsync(h->hOut, h->dOut, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(h->hOut, h->dOut, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
         h->stats[16] += h->hOut[3]; // singular triplets streamed by this pass (algorithmic-bytes accounting for bench.py)
         if (!*reinterpret_cast<const int *>(h->hOut + 4))
@@ -1664,7 +1697,7 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
             h->stats[18] += 1;
         }
     }
-    const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = 0.0;
+    const double s1 = h->hOut[0], s5 = h->hOut[1], s4 = h->hOut[2], s2 = h->cur_sumU, s3 = h->eps1f ? h->hOut[5] : 0.0;
     const double sigmasq = sigma * sigma;
     const double eps1 = 1.0 * 0.0001, eps2 = 100 * eps1;
     const double OoN = 1.0 / ((double)h->N * h->N * h->win);
