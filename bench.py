@@ -242,7 +242,9 @@ def main():
                 + (f", eps1_mode {args.eps1_mode}" if pgure else "")
                 + f"; step = block of {fps_step} frames (+{fw} halo frames each side) per GPU")
     config = {"workload": workload, "frames_per_step_per_gpu": fps_step, "frame_size": size, "sharding": "frames",
-              "l2_policy": "inputs larger than L2: each frame touches >= 4 GB of SVD factors (126 MB L2)"}
+              "l2_policy": "inputs larger than L2: every frame streams > 1 GB through the 126 MB L2 (three 126 MB windows, trajectories, "
+                           "leading-triplet records and head entries of 1.04 M patches, a 126 MB accumulator per evaluation), and consecutive "
+                           "steps re-upload and re-median the block"}
     metric = {3: "denoised frames/s (512^2, fixed lambda)", 4: "denoised frames/s (1024^2, PGURE lambda)",
               5: "denoised frames/s (4096^2, 64x31, PGURE lambda + ARPS)"}[args.config]
     if args.fixed_lambda and args.config != 3:
