@@ -1475,7 +1475,7 @@ static int objective_compact(pguresvt_handle *h, double lambda, double alpha, do
     int rc = compact_accumulate(h, lambda, -1, 1);
     if (rc)
         return rc;
-    k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart, h->evc_warps,
+    k_risk_uhat<0><<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart, h->evc_warps,
                                                 h->dPartial);
     LAUNCHED(h);
     k_reduce_partials<<<1, 256, 0, h->st>>>(h->dPartial, RISK_BLOCKS, 4, h->dOut);
@@ -1663,7 +1663,7 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
                                                                  h->p.exp_weighting, h->dAcc[1], h->dAccScale, nullptr, nullptr, SVD16_N, nullptr,
                                                                  tiled);
             LAUNCHED(h);
-            k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
+            k_risk_uhat<1><<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
                                                         4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0, h->dAcc[1], h->dD1,
                                                         alpha, sigmasq_e - alpha * mu, h->dPartial3);
             LAUNCHED(h);
@@ -1672,7 +1672,7 @@ static int objective_fused(pguresvt_handle *h, double lambda, double alpha, doub
         }
         else
         {
-            k_risk_uhat<<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
+            k_risk_uhat<0><<<RISK_BLOCKS, 256, 0, h->st>>>(h->dU, h->dCnt, h->dAcc[0], wtot, h->dAccScale, h->dPartialE, h->dKpart,
                                                         4 * cdiv(h->P, 8 * ppg_eff), h->dPartial, tiled ? (int)h->N : 0);
             LAUNCHED(h);
         }
